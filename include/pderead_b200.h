@@ -1,0 +1,181 @@
+/* pderead_b200.h -- C ABI of libpderead_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the data-parallel hot path of punkduckable/PDE-READ.  The reference is
+ * pure Python on PyTorch and has no FFI of its own; each entry point below states the reference
+ * function (file:line under /root/reference) whose work it replaces.  The Python package
+ * pde_read_b200/ keeps the reference's call signatures and binds these symbols with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller; the library never allocates
+ *     or frees device memory and keeps no state between calls;
+ *   - all tensors are contiguous row-major float32 unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - every function returns 0 on success or a negative pderead_status; no exceptions cross.
+ *   - workspace: query the *_workspace_bytes function, hand in a device buffer at least that
+ *     large (16-byte aligned).  A larger buffer lets the library process more points per chunk.
+ */
+#ifndef PDEREAD_B200_H
+#define PDEREAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDEREAD_MAX_HIDDEN_LAYERS 16
+#define PDEREAD_MAX_INPUT_DIM 8
+#define PDEREAD_MAX_SPATIAL_ORDER 4
+#define PDEREAD_MAX_TIME_ORDER 2
+#define PDEREAD_MAX_LIBRARY_COLUMNS 256
+
+typedef enum {
+    PDEREAD_OK = 0,
+    PDEREAD_ERR_BAD_ARGUMENT = -1,       /* null pointer, negative size, ... */
+    PDEREAD_ERR_UNSUPPORTED_ORDER = -2,  /* derivative orders outside the instantiated set */
+    PDEREAD_ERR_UNSUPPORTED_NET = -3,    /* width / depth / input dim / activation not supported */
+    PDEREAD_ERR_WORKSPACE_TOO_SMALL = -4,
+    PDEREAD_ERR_CUDA = -5,               /* a CUDA runtime call failed (see pderead_last_cuda_error) */
+    PDEREAD_ERR_NOT_BLACKWELL = -6       /* device is not compute capability 10.x */
+} pderead_status;
+
+typedef enum {
+    PDEREAD_ACT_TANH = 0,     /* torch.nn.Tanh              reference Network.py:158-160 */
+    PDEREAD_ACT_SIN = 1,      /* Sin.forward                reference Network.py:60-67   */
+    PDEREAD_ACT_RATIONAL = 2  /* Rational.forward (3,2)     reference Network.py:7-57    */
+} pderead_activation;
+
+/* One Neural_Network (reference Network.py:72-170): num_hidden_layers hidden Linear layers of
+ * `width` neurons with an activation after each, then a Linear to one output.
+ *   weight[i]: Layers[i].weight, row-major [out, in]  (i = 0 .. num_hidden_layers)
+ *   bias[i]  : Layers[i].bias
+ *   rat_a[i] : Activation_Functions[i].a [4], rat_b[i]: .b [3]  (Rational only, else NULL)
+ * pderead_net_grad has the same shape and receives d(loss)/d(parameter). */
+typedef struct {
+    int32_t num_hidden_layers;
+    int32_t width;
+    int32_t input_dim;
+    int32_t activation; /* pderead_activation */
+    const float* weight[PDEREAD_MAX_HIDDEN_LAYERS + 1];
+    const float* bias[PDEREAD_MAX_HIDDEN_LAYERS + 1];
+    const float* rat_a[PDEREAD_MAX_HIDDEN_LAYERS];
+    const float* rat_b[PDEREAD_MAX_HIDDEN_LAYERS];
+} pderead_net;
+
+typedef struct {
+    float* weight[PDEREAD_MAX_HIDDEN_LAYERS + 1];
+    float* bias[PDEREAD_MAX_HIDDEN_LAYERS + 1];
+    float* rat_a[PDEREAD_MAX_HIDDEN_LAYERS];
+    float* rat_b[PDEREAD_MAX_HIDDEN_LAYERS];
+} pderead_net_grad;
+
+const char* pderead_version(void);
+const char* pderead_status_string(int status);
+/* cudaError_t of the most recent failing CUDA call on this host thread (diagnostic only). */
+int pderead_last_cuda_error(void);
+
+/* ---- Evaluate_Derivatives: reference PDE_Residual.py:9-147 ------------------------------------
+ * d_coords [M,2] (col 0 = t, col 1 = x) -> d_dtm [M] = D_t^m U, d_dxn [M, n+1] = D_x^k U, k=0..n.
+ * time_order m in 0..2 (m = 0: d_dtm is not computed and may be NULL -- the extraction path,
+ * reference Extraction.py:305-341, never uses it); space_order n in 1..4 (or n = 0 with m = 0:
+ * plain network evaluation U(coords), the Data_Loss forward, reference Loss_Functions.py:115). */
+size_t pderead_sol_derivatives_workspace_bytes(const pderead_net* sol, int time_order, int space_order,
+                                               int64_t M, int need_backward);
+int pderead_sol_derivatives_forward(const pderead_net* sol, int time_order, int space_order,
+                                    const float* d_coords, int64_t M, float* d_dtm, float* d_dxn,
+                                    void* d_workspace, size_t workspace_bytes, void* stream);
+/* Reverse pass of the above (what Loss.backward() does through the nested autograd graph,
+ * reference Test_Train.py:99-100): given d_grad_dtm [M] (may be NULL = 0) and d_grad_dxn [M,n+1]
+ * (may be NULL = 0), writes grads = beta*grads + sum_points(...) for every parameter of `sol`. */
+int pderead_sol_derivatives_backward(const pderead_net* sol, int time_order, int space_order,
+                                     const float* d_coords, int64_t M, const float* d_grad_dtm,
+                                     const float* d_grad_dxn, const pderead_net_grad* grads, float beta,
+                                     void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Neural_Network.forward with scalar output: reference Network.py:174-202 ------------------
+ * d_in [M, input_dim] -> d_out [M].  Used for PDE_NN(Dxn_U) (reference PDE_Residual.py:211). */
+size_t pderead_mlp_workspace_bytes(const pderead_net* net, int64_t M, int need_backward);
+int pderead_mlp_forward(const pderead_net* net, const float* d_in, int64_t M, float* d_out,
+                        void* d_workspace, size_t workspace_bytes, void* stream);
+/* d_grad_out [M] -> parameter grads (beta as above) and, if d_grad_in != NULL, d_grad_in [M,input_dim]. */
+int pderead_mlp_backward(const pderead_net* net, const float* d_in, int64_t M, const float* d_grad_out,
+                         float* d_grad_in, const pderead_net_grad* grads, float beta,
+                         void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- PDE_Residual / Collocation_Loss: reference PDE_Residual.py:151-215, Loss_Functions.py:11-65
+ * R = D_t^m U - N(U, D_x U, .., D_x^n U) at d_coords [M,2].
+ *   d_resid [M]        : optional (NULL to skip)
+ *   d_sum_sq (double*) : optional; the launch ADDS sum(R^2) over these M points to *d_sum_sq
+ *                        (caller zeroes it; loss = *d_sum_sq / M_total). */
+size_t pderead_residual_workspace_bytes(const pderead_net* sol, const pderead_net* pde, int time_order,
+                                        int space_order, int64_t M, int need_backward);
+int pderead_residual_forward(const pderead_net* sol, const pderead_net* pde, int time_order, int space_order,
+                             const float* d_coords, int64_t M, float* d_resid, double* d_sum_sq,
+                             void* d_workspace, size_t workspace_bytes, void* stream);
+/* Collocation_Loss forward + Loss.backward() in one call (reference Test_Train.py:79-100 for the
+ * collocation term): loss = sum(R^2)/M_total over the M local points (M_total >= M lets several
+ * GPUs each take a shard; M_total = M on one GPU).  Adds sum(R^2) to *d_sum_sq and writes
+ * grads = beta*grads + d(sum(R^2)/M_total)/d(parameter) for both networks.
+ * If d_grad_resid != NULL it is used as d(loss)/dR [M] instead of 2R/M_total (PDE_Residual with an
+ * arbitrary downstream loss). */
+int pderead_collocation_loss_grad(const pderead_net* sol, const pderead_net* pde, int time_order,
+                                  int space_order, const float* d_coords, int64_t M, int64_t M_total,
+                                  const float* d_grad_resid, float* d_resid, double* d_sum_sq,
+                                  const pderead_net_grad* sol_grads, const pderead_net_grad* pde_grads,
+                                  float beta, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Extraction: reference Extraction.py:178-572 ----------------------------------------------
+ * Library columns are the monomials of (U, D_x U, .., D_x^n U) of degree <= poly_degree in the
+ * reference's order (Extraction.py:349-372); C = number of columns = binom(n+1+K, K). */
+int pderead_library_num_columns(int space_order, int poly_degree);
+/* multi-index table: h_indices [C, poly_degree] int32, padded with -1; row 0 is the constant. */
+int pderead_library_multi_indices(int space_order, int poly_degree, int32_t* h_indices);
+/* dense library (Generate_Library's second return value): d_dxn [M,n+1] -> d_library [M,C]. */
+int pderead_library_dense(const float* d_dxn, int64_t M, int space_order, int poly_degree,
+                          float* d_library, void* stream);
+/* Fused library + Gram: accumulates, in float64, G += A^T A [C,C], Atb += A^T b [C], btb += b^T b
+ * over M rows without materialising A.  Monomials are formed in float32 with the reference's
+ * left-to-right product order, then widened.  Outputs are ADDED to (caller zeroes them). */
+size_t pderead_library_gram_workspace_bytes(int space_order, int poly_degree);
+int pderead_library_gram(const float* d_dxn, const float* d_b, int64_t M, int space_order, int poly_degree,
+                         double* d_G, double* d_Atb, double* d_btb, void* d_workspace,
+                         size_t workspace_bytes, void* stream);
+/* Gram of an explicit matrix (for Recursive_Feature_Elimination(A, b) called with a dense A). */
+int pderead_dense_gram(const float* d_A, const float* d_b, int64_t M, int C, double* d_G, double* d_Atb,
+                       double* d_btb, void* d_workspace, size_t workspace_bytes, void* stream);
+/* Coords -> Gram in one call: U jets (no t-series), b = N(jets), fused library+Gram. */
+size_t pderead_extraction_gram_workspace_bytes(const pderead_net* sol, const pderead_net* pde, int space_order,
+                                               int poly_degree, int64_t M);
+int pderead_extraction_gram(const pderead_net* sol, const pderead_net* pde, int space_order, int poly_degree,
+                            const float* d_coords, int64_t M, double* d_G, double* d_Atb, double* d_btb,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
+/* Recursive_Feature_Elimination + Rank_Candidate_Solutions on the Gram system, on device
+ * (reference Extraction.py:382-501 and 505-572).  Inputs d_G [C,C], d_Atb [C], d_btb [1] (float64).
+ *   d_X [C,C] float32        : column j = j-th candidate (C-j non-zeros), un-scaled
+ *   d_residual [C+1] float32 : ||b - A x_j||_2, last = ||b||_2
+ *   d_order [C] int32        : feature eliminated at step j
+ *   d_rank [C] int32, d_change [C] float32 : Rank_Candidate_Solutions' permutation (ascending
+ *                              relative residual jump; last = most likely PDE) and sorted jumps. */
+size_t pderead_rfe_workspace_bytes(int C);
+int pderead_rfe_gram(const double* d_G, const double* d_Atb, const double* d_btb, int C, float* d_X,
+                     float* d_residual, int32_t* d_order, int32_t* d_rank, float* d_change,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Generate_Points: reference Points.py:7-62 --------------------------------------------------
+ * Uniform points in the box h_bounds [dim,2] (host, float64), Philox-4x32-10 counter stream
+ * (seed, offset + point index): distribution-equal, not bit-equal, to random.uniform. */
+int pderead_generate_points(const double* h_bounds, int dim, int64_t num_points, uint64_t seed,
+                            uint64_t offset, float* d_points, void* stream);
+
+/* ---- measurement helper ---------------------------------------------------------------------------
+ * Runs a register-resident FFMA loop on every SM (`iters` dependent FMA chains per thread) so that
+ * bench.py can measure the FP32 FMA peak that bounds this path.  variant 0: scalar FFMA,
+ * variant 1: packed fma.rn.f32x2.  *h_flops receives the FLOP count of the launch. */
+int pderead_fma_peak_probe(int variant, int iters, float* d_sink, double* h_flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDEREAD_B200_H */

@@ -1,0 +1,12 @@
+// One translation unit per (activation, NX, NT): compiled several times with
+//   -DPDR_ACT=<0|1|2> -DPDR_NX=<n> -DPDR_NT=<m> -DPDR_BWD=<0|1>
+// so that the template instantiations build in parallel (see pde_read_b200/build.py).
+#include "mlp_jet_kernels.cuh"
+
+namespace pdr {
+template int launch_fwd<PDR_ACT, PDR_NX, PDR_NT>(const FwdArgs&, cudaStream_t);
+#if PDR_BWD
+template int bwd_grid<PDR_ACT, PDR_NX, PDR_NT>(int, int, int, long long, int*);
+template int launch_bwd_impl<PDR_ACT, PDR_NX, PDR_NT>(const BwdArgs&, int, cudaStream_t);
+#endif
+}  // namespace pdr

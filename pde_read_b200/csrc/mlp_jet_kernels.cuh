@@ -1,0 +1,647 @@
+// Persistent MLP-jet kernels (sm_100a): forward of U / N with Taylor jets, and the matching
+// reverse pass for the parameter gradients.
+//
+// Replaces, for every collocation point, the chain
+//   Neural_Network.forward (reference Network.py:174-202)
+//   -> nested torch.autograd.grad in Evaluate_Derivatives (PDE_Residual.py:92-145)
+//   -> Loss.backward() (Test_Train.py:99-100)
+// by propagating the x-/t-series of every neuron through the layers (jet_math.cuh) and by the
+// hand-written adjoint of that propagation.
+//
+// Thread mapping ("lane = point"): a CTA owns a tile of TP = 32*PPL points; lane l of every warp
+// owns points l, l+32, ..; warp w owns chunks of TN output neurons.  In the layer product
+//   z_j[i] = sum_k W[i][k] h_j[k]      (j = jet index, i = output neuron)
+// a thread keeps PPL*J*TN accumulators in registers, reads h_j[k] of its own points from shared
+// memory (conflict-free: consecutive lanes -> consecutive words) and the TN weights W[i0..][k]
+// through the read-only path (same address in all lanes -> one broadcast transaction).  The
+// activation jets are then applied to the accumulators in registers; activations never go to HBM
+// except for the pre-activation stash the reverse pass needs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "internal.h"
+#include "jet_math.cuh"
+
+namespace pdr {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int ACT>
+__device__ __forceinline__ void load_ab(const NetDev& net, int l, float* ab) {
+    if (ACT == ACT_RATIONAL) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) ab[t] = __ldg(net.ra[l] + t);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) ab[4 + t] = __ldg(net.rb[l] + t);
+    } else {
+#pragma unroll
+        for (int t = 0; t < 7; ++t) ab[t] = 0.f;
+    }
+}
+
+// pre-activation jet of hidden layer 0 (the input layer) for neuron i at tile point pt:
+// z_0 = b + sum_d W[i][d] in[d];  the x-series is seeded by input column 1 and the t-series by
+// input column 0 (coords are (t, x), reference PDE_Residual.py:33-34).
+template <int NX, int NT>
+__device__ __forceinline__ void input_layer_jet(const NetDev& net, const float* IN, int TP, int i, int pt,
+                                                float* z) {
+    constexpr int J = 1 + NX + NT;
+    const float* wrow = net.w[0] + (size_t)i * net.din;
+    float s = __ldg(net.b[0] + i);
+    for (int d = 0; d < net.din; ++d) s = fmaf(__ldg(wrow + d), IN[d * TP + pt], s);
+#pragma unroll
+    for (int j = 0; j < J; ++j) z[j] = 0.f;
+    z[0] = s;
+    if (NX > 0) z[1] = __ldg(wrow + 1);
+    if (NT > 0) z[NX + 1] = __ldg(wrow + 0);
+}
+
+// =============================================================================================
+// forward
+// =============================================================================================
+template <int ACT, int NX, int NT, bool STASH>
+__global__ void __launch_bounds__(MAX_WARPS * 32) mlp_jet_fwd_kernel(const FwdArgs a) {
+    constexpr int J = 1 + NX + NT;
+    constexpr int PPL = PointsPerLane<J>::v;
+    constexpr int TP = 32 * PPL;
+    constexpr int HS = J * TP + 4;
+
+    extern __shared__ __align__(16) float smem[];
+    const NetDev& net = a.net;
+    const int W = net.W, L = net.L, din = net.din, NC = net.NC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+
+    float* Hbuf0 = smem;
+    float* Hbuf1 = Hbuf0 + (size_t)W * HS;
+    float* IN = Hbuf1 + (size_t)W * HS;
+    float* RED = IN + din * TP;   // [nwarps][J][TP]
+
+    double lsum = 0.0;
+    const float* wout = net.w[L];
+
+    for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const long long p0 = tile * TP;
+        for (int idx = threadIdx.x; idx < din * TP; idx += blockDim.x) {
+            const int pt = idx / din, d = idx - pt * din;
+            const long long p = p0 + pt;
+            IN[d * TP + pt] = (p < a.M) ? __ldg(a.in + p * din + d) : 0.f;
+        }
+        __syncthreads();
+
+        float part[PPL][J];
+#pragma unroll
+        for (int q = 0; q < PPL; ++q)
+#pragma unroll
+            for (int j = 0; j < J; ++j) part[q][j] = 0.f;
+
+        float* Hin = Hbuf0;
+        float* Hout = Hbuf1;
+        float ab[7];
+
+        // ---- hidden layer 0 -------------------------------------------------------------
+        load_ab<ACT>(net, 0, ab);
+        for (int c = warp; c < NC; c += nwarps) {
+#pragma unroll 1
+            for (int n = 0; n < TN; ++n) {
+                const int i = c * TN + n;
+                if (i >= W) break;
+                const float wo = (L == 1) ? __ldg(wout + i) : 0.f;
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) {
+                    const int pt = q * 32 + lane;
+                    float z[J], y[J];
+                    input_layer_jet<NX, NT>(net, IN, TP, i, pt, z);
+                    act_fwd<ACT, NX, NT, float>(z, ab, y);
+                    if (L == 1) {
+#pragma unroll
+                        for (int j = 0; j < J; ++j) part[q][j] = fmaf(wo, y[j], part[q][j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < J; ++j) Hin[(size_t)i * HS + j * TP + pt] = y[j];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- hidden layers 1 .. L-1 ------------------------------------------------------
+        for (int l = 1; l < L; ++l) {
+            const float* wp = a.wt_packed + (size_t)(l - 1) * W * NC * TNP;
+            const float* bias = net.b[l];
+            const bool last = (l == L - 1);
+            load_ab<ACT>(net, l, ab);
+            for (int c = warp; c < NC; c += nwarps) {
+                float acc[PPL][J][TN];
+#pragma unroll
+                for (int n = 0; n < TN; ++n) {
+                    const int i = c * TN + n;
+                    const float bv = (i < W) ? __ldg(bias + i) : 0.f;
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) {
+                        acc[q][0][n] = bv;
+#pragma unroll
+                        for (int j = 1; j < J; ++j) acc[q][j][n] = 0.f;
+                    }
+                }
+                const float* wk = wp + c * TNP;
+                const float* hk = Hin + lane;
+#pragma unroll 2
+                for (int k = 0; k < W; ++k) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(wk));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(wk) + 1);
+                    const float4 b2 = __ldg(reinterpret_cast<const float4*>(wk) + 2);
+                    const float bw[TNP] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            const float av = hk[j * TP + q * 32];
+#pragma unroll
+                            for (int n = 0; n < TN; ++n) acc[q][j][n] = fmaf(av, bw[n], acc[q][j][n]);
+                        }
+                    wk += NC * TNP;
+                    hk += HS;
+                }
+#pragma unroll
+                for (int n = 0; n < TN; ++n) {
+                    const int i = c * TN + n;
+                    if (i < W) {
+                        const float wo = last ? __ldg(wout + i) : 0.f;
+#pragma unroll
+                        for (int q = 0; q < PPL; ++q) {
+                            const int pt = q * 32 + lane;
+                            float z[J], y[J];
+#pragma unroll
+                            for (int j = 0; j < J; ++j) z[j] = acc[q][j][n];
+                            if (STASH) {
+                                float* sp = a.stash + (((size_t)tile * (L - 1) + (l - 1)) * W + i) * (J * TP) + pt;
+#pragma unroll
+                                for (int j = 0; j < J; ++j) sp[j * TP] = z[j];
+                            }
+                            act_fwd<ACT, NX, NT, float>(z, ab, y);
+                            if (last) {
+#pragma unroll
+                                for (int j = 0; j < J; ++j) part[q][j] = fmaf(wo, y[j], part[q][j]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < J; ++j) Hout[(size_t)i * HS + j * TP + pt] = y[j];
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            float* t = Hin; Hin = Hout; Hout = t;
+        }
+
+        // ---- output layer: reduce the per-warp partial dot products -----------------------
+#pragma unroll
+        for (int q = 0; q < PPL; ++q)
+#pragma unroll
+            for (int j = 0; j < J; ++j) RED[(warp * J + j) * TP + q * 32 + lane] = part[q][j];
+        __syncthreads();
+        const float bout = __ldg(net.b[L]);
+        for (int idx = threadIdx.x; idx < J * TP; idx += blockDim.x) {
+            const int j = idx / TP, pt = idx - j * TP;
+            const long long p = p0 + pt;
+            float u = (j == 0) ? bout : 0.f;
+            for (int w = 0; w < nwarps; ++w) u += RED[(w * J + j) * TP + pt];
+            if (p >= a.M) continue;
+            if (J == 1) {
+                if (a.dtm_in != nullptr) {
+                    const float R = __ldg(a.dtm_in + p) - u;
+                    if (a.resid_out) a.resid_out[p] = R;
+                    if (a.seed_out)
+                        a.seed_out[p] = (a.grad_resid != nullptr) ? -__ldg(a.grad_resid + p) : -a.seed_scale * R;
+                    lsum += (double)R * (double)R;
+                } else {
+                    a.out0[p] = u;
+                }
+            } else {
+                if (j <= NX) {
+                    float f = 1.f;
+#pragma unroll
+                    for (int t = 2; t <= NX; ++t) if (t <= j) f *= (float)t;
+                    a.out0[p * (NX + 1) + j] = u * f;
+                } else if (j == NX + NT && a.out1 != nullptr) {
+                    float f = 1.f;
+#pragma unroll
+                    for (int t = 2; t <= NT; ++t) f *= (float)t;
+                    a.out1[p] = u * f;
+                }
+            }
+        }
+        // RED / IN / H are next written only after further barriers of the next tile
+        __syncthreads();
+    }
+
+    if (J == 1 && a.sumsq != nullptr) {
+        // block reduction of the squared residuals (double), one atomic per CTA
+        __shared__ double red_d[MAX_WARPS];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+        if (lane == 0) red_d[warp] = lsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < nwarps; ++w) s += red_d[w];
+            atomicAdd(a.sumsq, s);
+        }
+    }
+}
+
+// =============================================================================================
+// backward
+// =============================================================================================
+
+// weight-gradient micro kernel: gW[i][k] += sum_r ZB[i][r] * HP[k][r],  r over (jet, point).
+// Thread-tile (mi, mk) owns rows i = mi + MI*ti and columns k = mk + MK*tk (strided, so that
+// consecutive lanes read consecutive shared-memory rows: row stride HS = 4 mod 32 words).
+template <int TI, int TK>
+__device__ __forceinline__ void wgrad_tiles(const float* __restrict__ ZB, const float* __restrict__ HP, int W,
+                                            int HS, int R, float* __restrict__ gw) {
+    const int MI = (W + TI - 1) / TI, MK = (W + TK - 1) / TK;
+    const int ntile = MI * MK;
+    for (int t = threadIdx.x; t < ntile; t += blockDim.x) {
+        const int mi = t / MK, mk = t - mi * MK;
+        const float4* ap[TI];
+        const float4* bp[TK];
+#pragma unroll
+        for (int ti = 0; ti < TI; ++ti) {
+            const int i = mi + MI * ti;
+            ap[ti] = reinterpret_cast<const float4*>(ZB + (size_t)(i < W ? i : mi) * HS);
+        }
+#pragma unroll
+        for (int tk = 0; tk < TK; ++tk) {
+            const int k = mk + MK * tk;
+            bp[tk] = reinterpret_cast<const float4*>(HP + (size_t)(k < W ? k : mk) * HS);
+        }
+        float acc[TI][TK];
+#pragma unroll
+        for (int ti = 0; ti < TI; ++ti)
+#pragma unroll
+            for (int tk = 0; tk < TK; ++tk) acc[ti][tk] = 0.f;
+        const int R4 = R >> 2;
+#pragma unroll 2
+        for (int r = 0; r < R4; ++r) {
+            float4 av[TI], bv[TK];
+#pragma unroll
+            for (int ti = 0; ti < TI; ++ti) av[ti] = ap[ti][r];
+#pragma unroll
+            for (int tk = 0; tk < TK; ++tk) bv[tk] = bp[tk][r];
+#pragma unroll
+            for (int ti = 0; ti < TI; ++ti)
+#pragma unroll
+                for (int tk = 0; tk < TK; ++tk) {
+                    float s = acc[ti][tk];
+                    s = fmaf(av[ti].x, bv[tk].x, s);
+                    s = fmaf(av[ti].y, bv[tk].y, s);
+                    s = fmaf(av[ti].z, bv[tk].z, s);
+                    s = fmaf(av[ti].w, bv[tk].w, s);
+                    acc[ti][tk] = s;
+                }
+        }
+#pragma unroll
+        for (int ti = 0; ti < TI; ++ti) {
+            const int i = mi + MI * ti;
+            if (i < W) {
+#pragma unroll
+                for (int tk = 0; tk < TK; ++tk) {
+                    const int k = mk + MK * tk;
+                    if (k < W) gw[(size_t)i * W + k] += acc[ti][tk];
+                }
+            }
+        }
+    }
+}
+
+template <int ACT, int NX, int NT>
+__global__ void __launch_bounds__(MAX_WARPS * 32) mlp_jet_bwd_kernel(const BwdArgs a) {
+    constexpr int J = 1 + NX + NT;
+    constexpr int PPL = PointsPerLane<J>::v;
+    constexpr int TP = 32 * PPL;
+    constexpr int HS = J * TP + 4;
+
+    extern __shared__ __align__(16) float smem[];
+    const NetDev& net = a.net;
+    const int W = net.W, L = net.L, din = net.din, NC = net.NC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+
+    float* ZB = smem;                          // adjoint of pre-activations of the current layer
+    float* HP = ZB + (size_t)W * HS;           // activations of the layer below / adjoint of them
+    float* IN = HP + (size_t)W * HS;           // [din][TP]
+    float* SD = IN + din * TP;                 // [J][TP] seeds = d(loss)/d(u_j), factorials folded in
+    float* GIN = SD + J * TP;                  // [din][TP]
+    float* SACC = GIN + din * TP;              // small-parameter gradient accumulators (persist over tiles)
+    const int sbL = L * W;                     // output bias
+    const int sw0 = sbL + 1;                   // input-layer weights [W][din]
+    const int swout = sw0 + W * din;           // output weights [W]
+    const int sab = swout + W;                 // rational coefficients [L][7]
+    const int NS = sab + 7 * L;
+
+    float* gp = a.gpart + (size_t)blockIdx.x * a.lay.total;
+    if (!a.accumulate)
+        for (int idx = threadIdx.x; idx < a.lay.total; idx += blockDim.x) gp[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < NS; idx += blockDim.x) SACC[idx] = 0.f;
+    __syncthreads();
+
+    const float* wout = net.w[L];
+
+    for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const long long p0 = tile * TP;
+        for (int idx = threadIdx.x; idx < din * TP; idx += blockDim.x) {
+            const int pt = idx / din, d = idx - pt * din;
+            const long long p = p0 + pt;
+            IN[d * TP + pt] = (p < a.M) ? __ldg(a.in + p * din + d) : 0.f;
+            GIN[d * TP + pt] = 0.f;
+        }
+        for (int idx = threadIdx.x; idx < J * TP; idx += blockDim.x) {
+            const int j = idx / TP, pt = idx - j * TP;
+            const long long p = p0 + pt;
+            float s = 0.f;
+            if (p < a.M) {
+                if (J == 1) {
+                    s = a.g0 ? a.g0_scale * __ldg(a.g0 + p) : 0.f;
+                } else if (j <= NX) {
+                    float f = 1.f;
+#pragma unroll
+                    for (int t = 2; t <= NX; ++t) if (t <= j) f *= (float)t;
+                    s = a.g0 ? a.g0_scale * f * __ldg(a.g0 + p * (NX + 1) + j) : 0.f;
+                } else if (j == NX + NT) {
+                    float f = 1.f;
+#pragma unroll
+                    for (int t = 2; t <= NT; ++t) f *= (float)t;
+                    s = a.g1 ? a.g1_scale * f * __ldg(a.g1 + p) : 0.f;
+                }
+            }
+            SD[idx] = s;
+        }
+        __syncthreads();
+
+        // output bias: d/d b_out = sum_p seed_0
+        if (warp == 0) {
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) s += SD[q * 32 + lane];
+            s = warp_sum(s);
+            if (lane == 0) SACC[sbL] += s;
+        }
+
+        // ---- VJP through hidden layer `lv` (top first).  ybar comes from the output layer
+        //      for the top layer, otherwise from HP (written by the product with W^T below).
+        for (int lv = L - 1; lv >= 0; --lv) {
+            const bool top = (lv == L - 1);
+            if (!top) {
+                const int l = lv + 1;   // weight matrix between hidden layers lv and lv+1
+                float ab_lo[7];
+                load_ab<ACT>(net, lv, ab_lo);
+                // (a) HP = h^{lv} = act(z^{lv})
+                for (int c = warp; c < NC; c += nwarps) {
+#pragma unroll 1
+                    for (int n = 0; n < TN; ++n) {
+                        const int i = c * TN + n;
+                        if (i >= W) break;
+#pragma unroll
+                        for (int q = 0; q < PPL; ++q) {
+                            const int pt = q * 32 + lane;
+                            float z[J], y[J];
+                            if (lv == 0) {
+                                input_layer_jet<NX, NT>(net, IN, TP, i, pt, z);
+                            } else {
+                                const float* sp = a.stash + (((size_t)tile * (L - 1) + (lv - 1)) * W + i) * (J * TP) + pt;
+#pragma unroll
+                                for (int j = 0; j < J; ++j) z[j] = __ldcs(sp + j * TP);
+                            }
+                            act_fwd<ACT, NX, NT, float>(z, ab_lo, y);
+#pragma unroll
+                            for (int j = 0; j < J; ++j) HP[(size_t)i * HS + j * TP + pt] = y[j];
+                        }
+                    }
+                }
+                __syncthreads();
+                // (b) weight gradient of matrix l:  gW[i][k] += sum_r ZB[i][r] HP[k][r]
+                {
+                    float* gw = gp + a.lay.off_w[l];
+                    if (a.wg_mode == 1) wgrad_tiles<5, 4>(ZB, HP, W, HS, J * TP, gw);
+                    else                wgrad_tiles<4, 4>(ZB, HP, W, HS, J * TP, gw);
+                }
+                __syncthreads();
+                // (c) HP = hbar^{lv}[k] = sum_i W_l[i][k] ZB[i]
+                const float* wp = a.wn_packed + (size_t)(l - 1) * W * NC * TNP;
+                for (int c = warp; c < NC; c += nwarps) {
+                    float acc[PPL][J][TN];
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                        for (int j = 0; j < J; ++j)
+#pragma unroll
+                            for (int n = 0; n < TN; ++n) acc[q][j][n] = 0.f;
+                    const float* wi = wp + c * TNP;
+                    const float* zi = ZB + lane;
+#pragma unroll 2
+                    for (int i = 0; i < W; ++i) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(wi));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(wi) + 1);
+                        const float4 b2 = __ldg(reinterpret_cast<const float4*>(wi) + 2);
+                        const float bw[TNP] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                        for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                            for (int j = 0; j < J; ++j) {
+                                const float av = zi[j * TP + q * 32];
+#pragma unroll
+                                for (int n = 0; n < TN; ++n) acc[q][j][n] = fmaf(av, bw[n], acc[q][j][n]);
+                            }
+                        wi += NC * TNP;
+                        zi += HS;
+                    }
+#pragma unroll
+                    for (int n = 0; n < TN; ++n) {
+                        const int k = c * TN + n;
+                        if (k < W) {
+#pragma unroll
+                            for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                                for (int j = 0; j < J; ++j) HP[(size_t)k * HS + j * TP + q * 32 + lane] = acc[q][j][n];
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+
+            // (d) VJP of the activation of hidden layer lv:  ZB = zbar^{lv}
+            float ab[7], abbar[7];
+            load_ab<ACT>(net, lv, ab);
+#pragma unroll
+            for (int t = 0; t < 7; ++t) abbar[t] = 0.f;
+            for (int c = warp; c < NC; c += nwarps) {
+#pragma unroll 1
+                for (int n = 0; n < TN; ++n) {
+                    const int i = c * TN + n;
+                    if (i >= W) break;
+                    const float wo = top ? __ldg(wout + i) : 0.f;
+                    float gb = 0.f, gwo = 0.f, gx = 0.f, gt = 0.f;
+                    float gwin[MAXD];
+#pragma unroll
+                    for (int d = 0; d < MAXD; ++d) gwin[d] = 0.f;
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) {
+                        const int pt = q * 32 + lane;
+                        float z[J], ybar[J], zbar[J];
+                        if (lv == 0) {
+                            input_layer_jet<NX, NT>(net, IN, TP, i, pt, z);
+                        } else {
+                            const float* sp = a.stash + (((size_t)tile * (L - 1) + (lv - 1)) * W + i) * (J * TP) + pt;
+#pragma unroll
+                            for (int j = 0; j < J; ++j) z[j] = __ldcs(sp + j * TP);
+                        }
+                        if (top) {
+                            float y[J];
+                            act_fwd<ACT, NX, NT, float>(z, ab, y);
+#pragma unroll
+                            for (int j = 0; j < J; ++j) {
+                                const float sd = SD[j * TP + pt];
+                                ybar[j] = wo * sd;
+                                gwo = fmaf(sd, y[j], gwo);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < J; ++j) ybar[j] = HP[(size_t)i * HS + j * TP + pt];
+                        }
+                        act_vjp<ACT, NX, NT, float>(z, ab, ybar, zbar, abbar);
+#pragma unroll
+                        for (int j = 0; j < J; ++j) ZB[(size_t)i * HS + j * TP + pt] = zbar[j];
+                        gb += zbar[0];
+                        if (lv == 0) {
+                            if (NX > 0) gx += zbar[1];
+                            if (NT > 0) gt += zbar[NX + 1];
+                            const float* wrow = net.w[0] + (size_t)i * din;
+#pragma unroll
+                            for (int d = 0; d < MAXD; ++d) {
+                                if (d < din) {
+                                    gwin[d] = fmaf(zbar[0], IN[d * TP + pt], gwin[d]);
+                                    if (a.gin != nullptr) atomicAdd(&GIN[d * TP + pt], __ldg(wrow + d) * zbar[0]);
+                                }
+                            }
+                        }
+                    }
+                    gb = warp_sum(gb);
+                    if (top) gwo = warp_sum(gwo);
+                    if (lv == 0) {
+                        if (NX > 0) gwin[1] += gx;
+                        if (NT > 0) gwin[0] += gt;
+#pragma unroll
+                        for (int d = 0; d < MAXD; ++d)
+                            if (d < din) gwin[d] = warp_sum(gwin[d]);
+                    }
+                    if (lane == 0) {
+                        SACC[lv * W + i] += gb;
+                        if (top) SACC[swout + i] += gwo;
+                        if (lv == 0) {
+#pragma unroll
+                            for (int d = 0; d < MAXD; ++d)
+                                if (d < din) SACC[sw0 + i * din + d] += gwin[d];
+                        }
+                    }
+                }
+            }
+            if (ACT == ACT_RATIONAL) {
+#pragma unroll
+                for (int t = 0; t < 7; ++t) {
+                    const float s = warp_sum(abbar[t]);
+                    if (lane == 0) atomicAdd(&SACC[sab + 7 * lv + t], s);
+                }
+            }
+            __syncthreads();
+        }
+
+        if (a.gin != nullptr) {
+            for (int idx = threadIdx.x; idx < din * TP; idx += blockDim.x) {
+                const int pt = idx / din, d = idx - pt * din;
+                const long long p = p0 + pt;
+                if (p < a.M) a.gin[p * din + d] = GIN[d * TP + pt];
+            }
+        }
+        __syncthreads();
+    }
+
+    // flush the small-parameter accumulators into this CTA's partial-gradient vector
+    for (int idx = threadIdx.x; idx < NS; idx += blockDim.x) {
+        int dst;
+        if (idx < sbL) {
+            const int l = idx / W;
+            dst = a.lay.off_b[l] + (idx - l * W);
+        } else if (idx == sbL) {
+            dst = a.lay.off_b[L];
+        } else if (idx < swout) {
+            dst = a.lay.off_w[0] + (idx - sw0);
+        } else if (idx < sab) {
+            dst = a.lay.off_w[L] + (idx - swout);
+        } else {
+            const int l = (idx - sab) / 7;
+            dst = a.lay.off_ab[l] + (idx - sab - 7 * l);
+        }
+        gp[dst] += SACC[idx];
+    }
+}
+
+// =============================================================================================
+// launchers
+// =============================================================================================
+inline int grid_for(const void* kernel, int threads, size_t smem, long long num_tiles, int* grid_out) {
+    int dev = 0, sms = 0, occ = 0;
+    PDR_CUDA_CHECK(cudaGetDevice(&dev));
+    PDR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    PDR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+    if (occ < 1) return PDEREAD_ERR_UNSUPPORTED_NET;
+    long long g = (long long)sms * occ;
+    if (g > num_tiles) g = num_tiles;
+    if (g < 1) g = 1;
+    *grid_out = (int)g;
+    return PDEREAD_OK;
+}
+
+template <int ACT, int NX, int NT>
+int launch_fwd(const FwdArgs& a, cudaStream_t stream) {
+    constexpr int J = 1 + NX + NT;
+    const int nw = block_warps(a.net.W);
+    const size_t smem = fwd_smem_bytes(a.net.W, a.net.din, J, nw);
+    const void* k = a.stash ? (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, true>
+                            : (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, false>;
+    int grid = 0;
+    int rc = grid_for(k, nw * 32, smem, a.num_tiles, &grid);
+    if (rc != PDEREAD_OK) return rc;
+    if (a.stash) mlp_jet_fwd_kernel<ACT, NX, NT, true><<<grid, nw * 32, smem, stream>>>(a);
+    else         mlp_jet_fwd_kernel<ACT, NX, NT, false><<<grid, nw * 32, smem, stream>>>(a);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    return PDEREAD_OK;
+}
+
+// The backward launch needs the grid size before the call (gpart is sized by it), so the
+// occupancy query and the launch are separate.
+template <int ACT, int NX, int NT>
+int bwd_grid(int W, int L, int din, long long num_tiles, int* grid_out) {
+    constexpr int J = 1 + NX + NT;
+    const int nw = block_warps(W);
+    const size_t smem = bwd_smem_bytes(W, L, din, J);
+    return grid_for((const void*)mlp_jet_bwd_kernel<ACT, NX, NT>, nw * 32, smem, num_tiles, grid_out);
+}
+
+template <int ACT, int NX, int NT>
+int launch_bwd_impl(const BwdArgs& a, int grid, cudaStream_t stream) {
+    constexpr int J = 1 + NX + NT;
+    const int nw = block_warps(a.net.W);
+    const size_t smem = bwd_smem_bytes(a.net.W, a.net.L, a.net.din, J);
+    PDR_CUDA_CHECK(cudaFuncSetAttribute((const void*)mlp_jet_bwd_kernel<ACT, NX, NT>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_jet_bwd_kernel<ACT, NX, NT><<<grid, nw * 32, smem, stream>>>(a);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    return PDEREAD_OK;
+}
+
+}  // namespace pdr

@@ -1,0 +1,157 @@
+"""GPU parity tests for Extraction mode: library, fused Gram, on-device RFE and ranking."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pde_read_oracle as orc
+from tests.helpers import load_golden, rel_err, split_state
+from tests.test_gpu_parity import DEV, make_net, to64
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,n,K", [("library_n1_k2.npz", 1, 2), ("library_n2_k3.npz", 2, 3), ("library_n3_k2.npz", 3, 2)])
+def test_generate_library_golden(name, n, K):
+    from pde_read_b200.Extraction import Generate_Library
+    z = load_golden(name)
+    U = make_net(split_state(z, "sol."), "Tanh", 2)
+    N = make_net(split_state(z, "pde."), "Tanh", n + 1)
+    b, Lib, counts, mil = Generate_Library(U, N, 1, n, torch.from_numpy(z["coords"]).to(DEV), K, DEV)
+    assert b.dtype == np.float32 and Lib.dtype == np.float32 and counts.dtype == np.int64
+    assert list(counts) == list(z["counts"])
+    for k in range(1, K + 1):
+        assert np.array_equal(mil[k], z["mi_%d" % k])
+    assert rel_err(b, z["b"]) < 1e-5
+    for c in range(Lib.shape[1]):
+        assert rel_err(Lib[:, c], z["Library"][:, c]) < 2e-5, c
+
+
+def test_library_closed_form_column_order():
+    """Reference Testing.py:436-489: n=1, K=2 library = [1, u, u_x, u^2, u u_x, u_x^2], tol 5e-5."""
+    from pde_read_b200.Extraction import Generate_Library
+    st = {"Layers.0.weight": torch.ones(5, 2), "Layers.0.bias": torch.ones(5),
+          "Layers.1.weight": torch.ones(1, 5), "Layers.1.bias": torch.ones(1)}
+    U = make_net(st, "Tanh", 2)
+    N = make_net(orc.init_network(2, 6, 2, "Tanh", seed=4), "Tanh", 2)
+    P = torch.rand(333, 2, generator=torch.Generator().manual_seed(5))
+    b, Lib, counts, mil = Generate_Library(U, N, 1, 1, P.to(DEV), 2, DEV)
+    th = np.tanh((P[:, 0] + P[:, 1] + 1.0).numpy().astype(np.float64))
+    u, ux = 5 * th + 1, 5 * (1 - th ** 2)
+    want = np.stack([np.ones_like(u), u, ux, u * u, u * ux, ux * ux], axis=1)
+    assert np.max(np.abs(Lib - want)) < 5e-5 * max(1.0, np.max(np.abs(want)))
+
+
+def test_multi_index_tables_match_library_kernel():
+    from pde_read_b200 import functional as F
+    from pde_read_b200.Extraction import Recursive_Counter, Recursive_Multi_Indices
+    for n, K in ((1, 2), (2, 3), (2, 5), (3, 5), (4, 5), (4, 1)):
+        tab = F.library_multi_indices(n, K)
+        cols = orc.library_columns(n, K)
+        assert tab.shape[0] == len(cols) == sum(Recursive_Counter(n + 1, k) for k in range(1, K + 1)) + 1
+        for c, mi in enumerate(cols):
+            assert tuple(int(v) for v in tab[c] if v >= 0) == mi
+        mi = np.empty((Recursive_Counter(n + 1, K), K), dtype=np.int64)
+        Recursive_Multi_Indices(mi, n + 1, K)
+        assert np.array_equal(mi, orc.multi_indices(n + 1, K))
+
+
+def test_gram_matches_float64_product():
+    from pde_read_b200 import functional as F
+    gen = torch.Generator().manual_seed(9)
+    for n, K, M in ((2, 3, 5000), (2, 5, 3333), (4, 5, 1500), (3, 4, 64)):
+        dxn = torch.randn(M, n + 1, generator=gen)
+        b = torch.randn(M, generator=gen)
+        lib = F.library_dense(dxn.to(DEV), n, K).cpu().numpy()
+        cols = orc.library_columns(n, K)
+        want = np.ones((M, len(cols)), dtype=np.float32)
+        for c, mi in enumerate(cols):
+            for idx in mi:
+                want[:, c] = want[:, c] * dxn[:, idx].numpy()
+        assert np.array_equal(lib, want)            # same float32 product order => bit-exact
+        G, Atb, btb = F.library_gram(dxn.to(DEV), b.to(DEV), n, K)
+        A64 = want.astype(np.float64)
+        assert rel_err(G.cpu().numpy(), A64.T @ A64) < 1e-12
+        assert rel_err(Atb.cpu().numpy(), A64.T @ b.numpy().astype(np.float64)) < 1e-12
+        assert abs(btb.item() - float((b.double() ** 2).sum())) < 1e-12 * btb.item()
+        G2, Atb2, btb2 = F.dense_gram(torch.from_numpy(want).to(DEV), b.to(DEV))
+        assert rel_err(G2.cpu().numpy(), G.cpu().numpy()) < 1e-13
+
+
+def test_extraction_golden_rfe_and_ranking(capsys):
+    """Shipped checkpoint, random.seed(0), 20000 points, K=3: same elimination
+    order, residuals, top-5 supports and printed #1 PDE as the reference."""
+    from pde_read_b200.Extraction import (Extract_PDE, Generate_Library, Print_Extracted_PDE, Rank_Candidate_Solutions,
+                                          Recursive_Feature_Elimination)
+    ck, z = load_golden("burgers_ckpt.npz"), load_golden("burgers_extract_k3.npz")
+    bounds = load_golden("burgers_data_loss.npz")["bounds"]
+    U = make_net(split_state(ck, "sol."), "Rational", 2)
+    N = make_net(split_state(ck, "pde."), "Rational", 3)
+    random.seed(0)
+    E = orc.generate_points(bounds, 20000)
+    assert np.array_equal(E[:512].numpy(), z["coords_head"])
+    # reference-shaped path: dense library on the device, RFE(A, b) on numpy arrays
+    b, Lib, counts, mil = Generate_Library(U, N, 1, 2, E.to(DEV), 3, DEV)
+    assert rel_err(b[:512], z["b_head"]) < 1e-5
+    assert rel_err(Lib[:512], z["lib_head"]) < 2e-5
+    X, Res = Recursive_Feature_Elimination(Lib, b)
+    Xr, Rr, chg = Rank_Candidate_Solutions(X, Res)
+    # fused path
+    fX, fRes, fXr, fRr, fchg, fcounts, fmil, order = Extract_PDE(U, N, 1, 2, E.to(DEV), 3)
+    want_order = [int(v) for v in z["order"]]
+    for got_X, got_Res, got_Xr, got_Rr, got_chg in ((X, Res, Xr, Rr, chg), (fX, fRes, fXr, fRr, fchg)):
+        np.testing.assert_allclose(got_Res, z["Residual"], rtol=2e-4)
+        # elimination order from the supports
+        got_order = []
+        for j in range(20):
+            sup = set(np.flatnonzero(got_X[:, j]).tolist())
+            nxt = set(np.flatnonzero(got_X[:, j + 1]).tolist()) if j + 1 < 20 else set()
+            got_order.append(sorted(sup - nxt)[0])
+        assert got_order == want_order
+        assert rel_err(got_X, z["X"]) < 1e-3
+        np.testing.assert_allclose(got_Rr, z["Residual_Ranked"], rtol=2e-4)
+        for j in range(15, 20):                      # top-5 supports identical
+            assert set(np.flatnonzero(got_Xr[:, j]).tolist()) == set(np.flatnonzero(z["X_Ranked"][:, j]).tolist())
+        best = got_Xr[:, -1]
+        assert set(np.flatnonzero(best).tolist()) == {3, 5}
+        assert abs(best[3] - 0.076364) < 1e-4 * 0.076364 + 2e-6 and abs(best[5] + 0.747831) < 1e-4 * 0.747831
+    assert [int(v) for v in order] == want_order
+    Print_Extracted_PDE(fXr[:, -1], 1, fcounts, fmil)
+    out = capsys.readouterr().out
+    assert out.startswith("D_t U = ") and "(D_x^2 U)" in out and "(U)(D_x U)" in out
+
+
+def test_rfe_gram_matches_oracle_on_random_problem():
+    """A well-conditioned synthetic regression: device RFE vs the reference-faithful numpy RFE."""
+    from pde_read_b200.Extraction import Rank_Candidate_Solutions, Recursive_Feature_Elimination
+    rng = np.random.default_rng(0)
+    M, C = 4000, 12
+    A = rng.normal(size=(M, C)).astype(np.float32) * rng.uniform(0.5, 3.0, size=C).astype(np.float32)
+    x_true = np.zeros(C, dtype=np.float32)
+    x_true[[1, 4, 7]] = [2.0, -1.0, 0.5]
+    b = (A @ x_true + 0.05 * rng.normal(size=M)).astype(np.float32)
+    X, Res = Recursive_Feature_Elimination(A, b)
+    Xo, Reso, order = orc.recursive_feature_elimination(A, b)
+    np.testing.assert_allclose(Res, Reso, rtol=1e-4)
+    assert rel_err(X, Xo) < 1e-4
+    Xr, Rr, chg = Rank_Candidate_Solutions(X, Res)
+    Xro, Rro, chgo, rank = orc.rank_candidate_solutions(Xo, Reso)
+    np.testing.assert_allclose(Rr, Rro, rtol=1e-4)
+    assert set(np.flatnonzero(Xr[:, -1]).tolist()) == {1, 4, 7}
+
+
+def test_generate_points_in_bounds_and_reproducible():
+    from pde_read_b200 import functional as F
+    bounds = np.array([[0.0, 10.0], [-8.0, 7.9375]])
+    P1 = F.generate_points(bounds, 200_000, DEV, seed=7)
+    P2 = F.generate_points(bounds, 200_000, DEV, seed=7)
+    P3 = F.generate_points(bounds, 100_000, DEV, seed=7, offset=100_000)
+    assert torch.equal(P1, P2) and torch.equal(P1[100_000:], P3)
+    assert P1[:, 0].min() >= 0.0 and P1[:, 0].max() <= 10.0
+    assert P1[:, 1].min() >= -8.0 and P1[:, 1].max() <= 7.9375
+    # uniformity: mean and variance of U(a,b)
+    for j, (lo, hi) in enumerate(bounds):
+        col = P1[:, j].double()
+        assert abs(col.mean().item() - (lo + hi) / 2) < 0.02 * (hi - lo)
+        assert abs(col.var().item() - (hi - lo) ** 2 / 12) < 0.02 * (hi - lo) ** 2

@@ -1,0 +1,316 @@
+"""GPU parity tests: the CUDA path (through the Python mirror of the reference API, i.e. through
+the C ABI) against the golden vectors of the unmodified reference and against the CPU oracle.
+
+Stated tolerances, metric max|ours-ref|/max|ref| per output column:
+derivative order 0-2: 1e-5, order 3: 2e-5, order 4: 5e-5, residual and gradients: 1e-4; a result
+closer to the float64 reference than the float32 reference itself is accepted.
+"""
+import glob
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pde_read_oracle as orc
+from tests.helpers import (GOLDEN, TOL_GRAD, TOL_LOSS, TOL_ORDER, TOL_RESIDUAL, assert_close_to_reference, load_golden,
+                           rel_err, split_state)
+
+pytestmark = pytest.mark.gpu
+
+DEV = torch.device("cuda:0")
+
+
+def make_net(state, act, din):
+    from pde_read_b200.Network import Neural_Network
+    L = orc.num_hidden_layers(state)
+    W = state["Layers.0.weight"].shape[0]
+    net = Neural_Network(L, W, din, 1, Data_Type=torch.float32, Device=DEV, Activation_Function=act)
+    net.load_state_dict({k: v.to(DEV) for k, v in state.items()})
+    return net
+
+
+def grads_of(net):
+    return {k: (p.grad.detach().cpu().numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32))
+            for k, p in net.named_parameters()}
+
+
+def to64(state):
+    return {k: v.double() for k, v in state.items()}
+
+
+# ----------------------------------------------------------------------------------------------
+def test_library_loads_and_reports_version():
+    from pde_read_b200 import _lib
+    lib = _lib.load()
+    assert b"sm_100a" in lib.pderead_version()
+
+
+def test_closed_form_ones_network():
+    """Reference Testing.py:253-300 formulas: u = n tanh(t+x+1)+1, u_t = u_x = n(1-tanh^2),
+    u_xx = -2 n tanh (1-tanh^2); tolerances Epsilon*5 / *10 / *15 with Epsilon = 5e-6."""
+    from pde_read_b200.PDE_Residual import Evaluate_Derivatives
+    n_h = 9
+    st = {"Layers.0.weight": torch.ones(n_h, 2), "Layers.0.bias": torch.ones(n_h),
+          "Layers.1.weight": torch.ones(1, n_h), "Layers.1.bias": torch.ones(1)}
+    net = make_net(st, "Tanh", 2)
+    P = torch.rand(777, 2, generator=torch.Generator().manual_seed(3))
+    Dtm, Dxn = Evaluate_Derivatives(net, 1, 2, P.to(DEV), torch.float32, DEV)
+    th = torch.tanh(P[:, 0].double() + P[:, 1].double() + 1.0)
+    eps = 5e-6
+    assert (Dxn[:, 0].cpu() - (n_h * th + 1)).abs().max().item() < 5 * eps
+    assert (Dtm.cpu() - n_h * (1 - th ** 2)).abs().max().item() < 10 * eps
+    assert (Dxn[:, 1].cpu() - n_h * (1 - th ** 2)).abs().max().item() < 10 * eps
+    assert (Dxn[:, 2].cpu() - (-2 * n_h * th * (1 - th ** 2))).abs().max().item() < 15 * eps
+
+
+def test_network_forward_matches_oracle():
+    from pde_read_b200.Network import Neural_Network
+    for act in ("Tanh", "Sin", "Rational"):
+        for (L, W, din) in ((1, 7, 2), (3, 33, 3), (5, 50, 2), (2, 100, 5), (4, 128, 1)):
+            st = orc.init_network(L, W, din, act, seed=L * 100 + W)
+            net = make_net(st, act, din)
+            X = torch.randn(1000 + W, din, generator=torch.Generator().manual_seed(W))
+            got = net(X.to(DEV)).cpu()
+            want = orc.network_forward(st, act, X)
+            want64 = orc.network_forward(to64(st), act, X.double())
+            assert got.shape == want.shape
+            assert_close_to_reference(got.numpy(), want.numpy(), want64.numpy(), 1e-5, "%s L%d W%d" % (act, L, W))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "random_*.npz"))))
+def test_random_nets_match_reference_golden(path):
+    from pde_read_b200.Loss_Functions import Collocation_Loss
+    from pde_read_b200.PDE_Residual import Evaluate_Derivatives, PDE_Residual
+    z = np.load(path)
+    LU, WU, LN, WN, m, n = [int(v) for v in z["meta"]]
+    aU, aN = [str(v) for v in z["acts"]]
+    U = make_net(split_state(z, "sol."), aU, 2)
+    N = make_net(split_state(z, "pde."), aN, n + 1)
+    P = torch.from_numpy(z["coords"]).to(DEV)
+    Dtm, Dxn = Evaluate_Derivatives(U, m, n, P, torch.float32, DEV)
+    name = os.path.basename(path)
+    assert_close_to_reference(Dtm.detach().cpu().numpy(), z["dtm"], z["dtm_f64"], TOL_ORDER[min(m, 4)], name + " dtm")
+    for k in range(n + 1):
+        assert_close_to_reference(Dxn[:, k].detach().cpu().numpy(), z["dxn"][:, k], z["dxn_f64"][:, k], TOL_ORDER[k],
+                                  name + " dxn[%d]" % k)
+    R = PDE_Residual(U, N, m, n, P, torch.float32, DEV)
+    assert_close_to_reference(R.detach().cpu().numpy(), z["resid"], z["resid_f64"], TOL_RESIDUAL, name + " residual")
+    loss = Collocation_Loss(U, N, m, n, P, torch.float32, DEV)
+    assert loss.dtype == torch.float32 and loss.dim() == 0
+    assert abs(loss.item() - float(z["loss"])) <= 2e-5 * abs(float(z["loss"]))
+    loss.backward()
+    for pref, net in (("gsol.", U), ("gpde.", N)):
+        for k, g in grads_of(net).items():
+            assert_close_to_reference(g, z[pref + k], z[pref + k + ".f64"], TOL_GRAD, name + " " + pref + k)
+
+
+def test_residual_autograd_matches_loss_autograd():
+    """(PDE_Residual ** 2).mean().backward() must give the same gradients as Collocation_Loss."""
+    from pde_read_b200.Loss_Functions import Collocation_Loss
+    from pde_read_b200.PDE_Residual import PDE_Residual
+    z = load_golden("random_rat_m1n3.npz")
+    U = make_net(split_state(z, "sol."), "Rational", 2)
+    N = make_net(split_state(z, "pde."), "Rational", 4)
+    P = torch.from_numpy(z["coords"]).to(DEV)
+    (PDE_Residual(U, N, 1, 3, P, torch.float32, DEV) ** 2).mean().backward()
+    g1 = {**{"u." + k: v for k, v in grads_of(U).items()}, **{"n." + k: v for k, v in grads_of(N).items()}}
+    U.zero_grad(); N.zero_grad()
+    Collocation_Loss(U, N, 1, 3, P, torch.float32, DEV).backward()
+    g2 = {**{"u." + k: v for k, v in grads_of(U).items()}, **{"n." + k: v for k, v in grads_of(N).items()}}
+    for k in g1:
+        assert rel_err(g1[k], g2[k]) < 2e-5, k
+
+
+def test_evaluate_derivatives_autograd():
+    """Gradients flowing back through (Dtm_U, Dxn_U) with arbitrary weights, vs the oracle."""
+    from pde_read_b200.PDE_Residual import Evaluate_Derivatives
+    z = load_golden("random_tanh_m2n3.npz")
+    st = split_state(z, "sol.")
+    U = make_net(st, "Tanh", 2)
+    P = torch.from_numpy(z["coords"])
+    gen = torch.Generator().manual_seed(5)
+    w_t, w_x = torch.randn(P.shape[0], generator=gen), torch.randn(P.shape[0], 4, generator=gen)
+    Dtm, Dxn = Evaluate_Derivatives(U, 2, 3, P.to(DEV), torch.float32, DEV)
+    ((Dtm * w_t.to(DEV)).sum() + (Dxn * w_x.to(DEV)).sum()).backward()
+    S = {k: v.clone().double().requires_grad_(True) for k, v in st.items()}
+    d64, x64 = orc.evaluate_derivatives(S, "Tanh", 2, 3, P.double())
+    ((d64 * w_t.double()).sum() + (x64 * w_x.double()).sum()).backward()
+    for k, g in grads_of(U).items():
+        assert rel_err(g, S[k].grad.numpy()) < TOL_GRAD, k
+
+
+def test_checkpoint_collocation_golden():
+    """Shipped Burgers checkpoint, 5000 seeded points."""
+    from pde_read_b200.Loss_Functions import Collocation_Loss
+    from pde_read_b200.PDE_Residual import Evaluate_Derivatives, PDE_Residual
+    ck, z = load_golden("burgers_ckpt.npz"), load_golden("burgers_colloc.npz")
+    U = make_net(split_state(ck, "sol."), "Rational", 2)
+    N = make_net(split_state(ck, "pde."), "Rational", 3)
+    P = torch.from_numpy(z["coords"]).to(DEV)
+    H = z["dtm"].shape[0]
+    Dtm, Dxn = Evaluate_Derivatives(U, 1, 2, P, torch.float32, DEV)
+    assert_close_to_reference(Dtm[:H].detach().cpu().numpy(), z["dtm"], z["dtm_f64"], 1e-5, "dtm")
+    for k in range(3):
+        assert_close_to_reference(Dxn[:H, k].detach().cpu().numpy(), z["dxn"][:, k], z["dxn_f64"][:, k], 1e-5, "dxn%d" % k)
+    R = PDE_Residual(U, N, 1, 2, P, torch.float32, DEV)
+    assert_close_to_reference(R[:H].detach().cpu().numpy(), z["resid"], z["resid_f64"], TOL_RESIDUAL, "resid")
+    loss = Collocation_Loss(U, N, 1, 2, P, torch.float32, DEV)
+    assert abs(loss.item() - 3.229976e-4) < 3e-9
+    loss.backward()
+    for pref, net in (("gsol.", U), ("gpde.", N)):
+        for k, g in grads_of(net).items():
+            assert_close_to_reference(g, z[pref + k], z[pref + k + ".f64"], TOL_GRAD, pref + k)
+
+
+def test_data_loss_golden():
+    from pde_read_b200.Loss_Functions import Data_Loss
+    ck, z = load_golden("burgers_ckpt.npz"), load_golden("burgers_data_loss.npz")
+    U = make_net(split_state(ck, "sol."), "Rational", 2)
+    loss = Data_Loss(U, torch.from_numpy(z["inputs"]).to(DEV), torch.from_numpy(z["targets"]).to(DEV), torch.float32, DEV)
+    assert loss.dtype == torch.float64
+    assert abs(loss.item() - float(z["loss"])) < 1e-6 * float(z["loss"])
+    loss.backward()
+    for k, g in grads_of(U).items():
+        assert rel_err(g, z["gsol." + k]) < TOL_GRAD, k
+
+
+def test_total_loss_closure_like_reference():
+    """Collocation + Data loss summed and back-propagated once, as Discovery_Closure does."""
+    from pde_read_b200.Loss_Functions import Collocation_Loss, Data_Loss
+    ck, zc, zd = load_golden("burgers_ckpt.npz"), load_golden("burgers_colloc.npz"), load_golden("burgers_data_loss.npz")
+    U = make_net(split_state(ck, "sol."), "Rational", 2)
+    N = make_net(split_state(ck, "pde."), "Rational", 3)
+    P = torch.from_numpy(zc["coords"]).to(DEV)
+    total = Collocation_Loss(U, N, 1, 2, P, torch.float32, DEV) + \
+        Data_Loss(U, torch.from_numpy(zd["inputs"]).to(DEV), torch.from_numpy(zd["targets"]).to(DEV), torch.float32, DEV)
+    assert total.dtype == torch.float64
+    total.backward()
+    for k, g in grads_of(U).items():
+        want = zc["gsol." + k].astype(np.float64) + zd["gsol." + k].astype(np.float64)
+        assert rel_err(g, want) < TOL_GRAD, k
+    for k, g in grads_of(N).items():
+        assert_close_to_reference(g, zc["gpde." + k], zc["gpde." + k + ".f64"], TOL_GRAD, k)
+
+
+@pytest.mark.parametrize("act,LU,WU,LN,WN,m,n,M", [
+    ("Tanh", 5, 50, 5, 50, 1, 2, 3000),        # config 2 shape (heat)
+    ("Rational", 5, 50, 5, 50, 1, 3, 2000),    # config 3 shape (KdV)
+    ("Rational", 5, 100, 5, 100, 1, 4, 700),   # config 4 shape (KS)
+    ("Tanh", 5, 100, 5, 100, 1, 4, 700),
+    ("Sin", 3, 64, 2, 40, 2, 2, 1111),
+])
+def test_bench_shapes_match_oracle(act, LU, WU, LN, WN, m, n, M):
+    """Random-init nets of the benchmark shapes against the live CPU oracle (fp32 and fp64)."""
+    from pde_read_b200.Loss_Functions import Collocation_Loss
+    from pde_read_b200.PDE_Residual import Evaluate_Derivatives
+    su = orc.init_network(LU, WU, 2, act, seed=11)
+    sn = orc.init_network(LN, WN, n + 1, act, seed=12)
+    U, N = make_net(su, act, 2), make_net(sn, act, n + 1)
+    gen = torch.Generator().manual_seed(13)
+    P = torch.rand(M, 2, generator=gen) * torch.tensor([1.0, 2.0]) + torch.tensor([0.0, -1.0])
+    Dtm, Dxn = Evaluate_Derivatives(U, m, n, P.to(DEV), torch.float32, DEV)
+    d32, x32 = orc.evaluate_derivatives(su, act, m, n, P, create_graph=False)
+    d64, x64 = orc.evaluate_derivatives(to64(su), act, m, n, P.double(), create_graph=False)
+    assert_close_to_reference(Dtm.detach().cpu().numpy(), d32.numpy(), d64.numpy(), TOL_ORDER[m], "dtm")
+    for k in range(n + 1):
+        assert_close_to_reference(Dxn[:, k].detach().cpu().numpy(), x32[:, k].numpy(), x64[:, k].numpy(), TOL_ORDER[k],
+                                  "dxn%d" % k)
+    loss = Collocation_Loss(U, N, m, n, P.to(DEV), torch.float32, DEV)
+    loss.backward()
+    l32, gs32, gp32 = orc.collocation_loss_and_grads(su, act, sn, act, m, n, P, chunk=1000)
+    l64, gs64, gp64 = orc.collocation_loss_and_grads(to64(su), act, to64(sn), act, m, n, P.double(), chunk=1000)
+    assert abs(loss.item() - l64) <= max(TOL_LOSS * abs(l64), 1.5 * abs(l32 - l64))
+    for pref, net, g32, g64 in (("u.", U, gs32, gs64), ("n.", N, gp32, gp64)):
+        for k, g in grads_of(net).items():
+            assert_close_to_reference(g, g32[k].numpy(), g64[k].numpy(), TOL_GRAD, pref + k)
+
+
+@pytest.mark.parametrize("M", [0, 1, 31, 32, 33, 127, 128, 129, 1000])
+def test_ragged_and_empty_point_sets(M):
+    from pde_read_b200.Loss_Functions import Collocation_Loss
+    from pde_read_b200.PDE_Residual import PDE_Residual
+    z = load_golden("random_tanh_m1n2.npz")
+    su, sn = split_state(z, "sol."), split_state(z, "pde.")
+    U, N = make_net(su, "Tanh", 2), make_net(sn, "Tanh", 3)
+    P = torch.rand(M, 2, generator=torch.Generator().manual_seed(M))
+    R = PDE_Residual(U, N, 1, 2, P.to(DEV), torch.float32, DEV)
+    assert R.shape == (M,)
+    if M == 0:
+        return
+    want = orc.pde_residual(to64(su), "Tanh", to64(sn), "Tanh", 1, 2, P.double()).detach()
+    assert rel_err(R.detach().cpu().numpy(), want.numpy()) < TOL_RESIDUAL
+    Collocation_Loss(U, N, 1, 2, P.to(DEV), torch.float32, DEV).backward()
+    _, gs, gp = orc.collocation_loss_and_grads(to64(su), "Tanh", to64(sn), "Tanh", 1, 2, P.double())
+    for k, g in grads_of(U).items():
+        assert rel_err(g, gs[k].numpy()) < TOL_GRAD, k
+    for k, g in grads_of(N).items():
+        assert rel_err(g, gp[k].numpy()) < TOL_GRAD, k
+
+
+def test_chunked_workspace_gives_same_result():
+    """A workspace that only fits a few hundred points per chunk must not change loss or grads."""
+    from pde_read_b200 import functional as F
+    z = load_golden("random_rat_m2n2.npz")
+    su, sn = split_state(z, "sol."), split_state(z, "pde.")
+    U, N = make_net(su, "Rational", 2), make_net(sn, "Rational", 3)
+    P = (torch.rand(5000, 2, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(DEV)
+    spec_u, spec_n = F.net_spec(U), F.net_spec(N)
+    tu, tn = F.net_tensors(U), F.net_tensors(N)
+    ss1, flat1, *_ = F.collocation_loss_grad(spec_u, tu, spec_n, tn, 2, 2, P)
+    old = F.WORKSPACE_CAP_POINTS
+    try:
+        F.WORKSPACE_CAP_POINTS = 384
+        F.release_workspaces()
+        ss2, flat2, *_ = F.collocation_loss_grad(spec_u, tu, spec_n, tn, 2, 2, P)
+    finally:
+        F.WORKSPACE_CAP_POINTS = old
+        F.release_workspaces()
+    assert abs(ss1.item() - ss2.item()) <= 1e-6 * abs(ss1.item())
+    assert rel_err(flat2.cpu().numpy(), flat1.cpu().numpy()) < 2e-5
+
+
+def test_full_size_properties():
+    """Size-independent properties at a benchmark-sized point set (1e5 points, config 2 shape):
+    permutation equivariance of R and additivity of sum(R^2) and of the gradients over shards."""
+    from pde_read_b200 import functional as F
+    su = orc.init_network(5, 50, 2, "Tanh", seed=21)
+    sn = orc.init_network(5, 50, 3, "Tanh", seed=22)
+    U, N = make_net(su, "Tanh", 2), make_net(sn, "Tanh", 3)
+    M = 100_000
+    P = (torch.rand(M, 2, generator=torch.Generator().manual_seed(2)) * torch.tensor([10.0, 9.95])).to(DEV)
+    spec_u, spec_n = F.net_spec(U), F.net_spec(N)
+    tu, tn = F.net_tensors(U), F.net_tensors(N)
+    R, ss = F.residual_forward(spec_u, tu, spec_n, tn, 1, 2, P)
+    perm = torch.randperm(M, generator=torch.Generator().manual_seed(3)).to(DEV)
+    Rp, ssp = F.residual_forward(spec_u, tu, spec_n, tn, 1, 2, P[perm].contiguous())
+    assert torch.equal(Rp, R[perm])
+    assert abs(ss.item() - (R.double() ** 2).sum().item()) <= 1e-9 * ss.item()
+    ss_all, flat_all, *_ = F.collocation_loss_grad(spec_u, tu, spec_n, tn, 1, 2, P)
+    cut = 37_123
+    ss_a, flat_a, *_ = F.collocation_loss_grad(spec_u, tu, spec_n, tn, 1, 2, P[:cut].contiguous(), M_total=M)
+    ss_b, flat_b, *_ = F.collocation_loss_grad(spec_u, tu, spec_n, tn, 1, 2, P[cut:].contiguous(), M_total=M)
+    assert abs(ss_all.item() - ss_a.item() - ss_b.item()) <= 1e-9 * ss_all.item()
+    assert rel_err((flat_a + flat_b).cpu().numpy(), flat_all.cpu().numpy()) < 2e-5
+    # spot-check 512 points against the float64 oracle
+    idx = torch.arange(0, M, M // 512)[:512]
+    want = orc.pde_residual(to64(su), "Tanh", to64(sn), "Tanh", 1, 2, P[idx.to(DEV)].cpu().double()).detach()
+    assert rel_err(R[idx.to(DEV)].cpu().numpy(), want.numpy()) < TOL_RESIDUAL
+
+
+def test_unsupported_inputs_fail_loudly():
+    from pde_read_b200 import functional as F
+    from pde_read_b200.Network import Neural_Network
+    from pde_read_b200.PDE_Residual import Evaluate_Derivatives
+    cpu_net = Neural_Network(2, 8, 2, 1, Activation_Function="Tanh")
+    with pytest.raises(F.PdereadError):
+        cpu_net(torch.rand(4, 2))                       # CPU tensors: no fallback
+    net = Neural_Network(2, 8, 2, 1, Device=DEV, Activation_Function="Tanh")
+    with pytest.raises(F.PdereadError):
+        Evaluate_Derivatives(net, 1, 7, torch.rand(4, 2, device=DEV), torch.float32, DEV)   # order not instantiated
+    with pytest.raises(NotImplementedError):
+        Evaluate_Derivatives(net, 1, 2, torch.rand(4, 2, device=DEV), torch.float64, DEV)
+    bn = Neural_Network(2, 8, 3, 1, Device=DEV, Activation_Function="Tanh", Batch_Norm=True)
+    with pytest.raises(NotImplementedError):
+        bn(torch.rand(4, 3, device=DEV))
