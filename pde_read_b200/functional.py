@@ -370,7 +370,8 @@ class CollocationLossFn(torch.autograd.Function):
     def forward(ctx, coords, sol_spec, pde_spec, m, n, n_sol, reducer, *tensors):
         sol_t, pde_t = tensors[:n_sol], tensors[n_sol:]
         M = coords.shape[0]
-        need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+        # (grad mode is always off inside Function.forward; needs_input_grad is the real signal)
+        need_grad = any(ctx.needs_input_grad[7:])
         M_total = reducer.total_points(M) if reducer is not None else M
         if need_grad:
             ss, flat, vu, vn, _ = collocation_loss_grad(sol_spec, sol_t, pde_spec, pde_t, m, n, coords,
@@ -383,7 +384,7 @@ class CollocationLossFn(torch.autograd.Function):
             if reducer is not None:
                 ss = reducer.reduce(None, ss)
         ctx.need_grad = need_grad
-        ctx.flags = [t.requires_grad for t in tensors]
+        ctx.flags = list(ctx.needs_input_grad[7:])
         loss = (ss / float(M_total)).to(torch.float32).reshape(())
         return loss
 

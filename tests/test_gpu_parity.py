@@ -72,7 +72,7 @@ def test_network_forward_matches_oracle():
             st = orc.init_network(L, W, din, act, seed=L * 100 + W)
             net = make_net(st, act, din)
             X = torch.randn(1000 + W, din, generator=torch.Generator().manual_seed(W))
-            got = net(X.to(DEV)).cpu()
+            got = net(X.to(DEV)).detach().cpu()
             want = orc.network_forward(st, act, X)
             want64 = orc.network_forward(to64(st), act, X.double())
             assert got.shape == want.shape
