@@ -174,6 +174,12 @@ int pderead_generate_points(const double* h_bounds, int dim, int64_t num_points,
  * bench.py can measure the FP32 FMA peak that bounds this path.  variant 0: scalar FFMA,
  * variant 1: packed fma.rn.f32x2.  *h_flops receives the FLOP count of the launch. */
 int pderead_fma_peak_probe(int variant, int iters, float* d_sink, double* h_flops, void* stream);
+/* Hand the library `count` caller-created cudaEvent_t (host array).  Every kernel the following
+ * calls on this host thread launch is followed by cudaEventRecord(events[i++], stream) until the
+ * array is used up; pass NULL to stop.  Lets bench.py time individual kernels inside a normal step
+ * without synchronising.  pderead_debug_stage_events_recorded() returns how many were recorded. */
+int pderead_debug_stage_events(void* const* events, int count);
+int pderead_debug_stage_events_recorded(void);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,8 @@ PROTOTYPES = {
                                  c_void_p, c_size_t, c_void_p]),
     "pderead_generate_points": (c_int, [POINTER(c_double), c_int, c_int64, c_uint64, c_uint64, c_void_p, c_void_p]),
     "pderead_fma_peak_probe": (c_int, [c_int, c_int, c_void_p, POINTER(c_double), c_void_p]),
+    "pderead_debug_stage_events": (c_int, [POINTER(c_void_p), c_int]),
+    "pderead_debug_stage_events_recorded": (c_int, []),
 }
 
 _lib = None

@@ -10,6 +10,15 @@ namespace pdr {
 static thread_local int g_last_cuda_error = 0;
 void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = (int)e; }
 
+// Optional measurement hook (bench.py): a caller-owned array of cudaEvent_t that the next calls on
+// this host thread record, one after every kernel launch, so individual kernels can be timed
+// inside an otherwise unmodified step without synchronising.
+static thread_local cudaEvent_t* g_stage_events = nullptr;
+static thread_local int g_stage_count = 0, g_stage_next = 0;
+void stage_mark(cudaStream_t s) {
+    if (g_stage_events && g_stage_next < g_stage_count) cudaEventRecord(g_stage_events[g_stage_next++], s);
+}
+
 int block_warps(int W) {
     const int NC = (W + TN - 1) / TN;
     return NC < MAX_WARPS ? NC : MAX_WARPS;
@@ -215,7 +224,7 @@ static bool order_supported(int nx, int nt) {
 #define PDR_FWD_COMBOS(X) X(0, 0) X(1, 0) X(2, 0) X(3, 0) X(4, 0) X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(1, 2) X(2, 2) X(3, 2) X(4, 2)
 #define PDR_BWD_COMBOS(X) X(0, 0) X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(1, 2) X(2, 2) X(3, 2) X(4, 2)
 
-static int dispatch_fwd(int act, int nx, int nt, const FwdArgs& a, cudaStream_t s) {
+static int dispatch_fwd_raw(int act, int nx, int nt, const FwdArgs& a, cudaStream_t s) {
 #define CASE(X_, T_)                                                   \
     if (nx == X_ && nt == T_) {                                        \
         switch (act) {                                                 \
@@ -243,7 +252,7 @@ static int dispatch_bwd_grid(int act, int nx, int nt, int W, int L, int din, lon
     return PDEREAD_ERR_UNSUPPORTED_ORDER;
 }
 
-static int dispatch_bwd(int act, int nx, int nt, const BwdArgs& a, int grid, cudaStream_t s) {
+static int dispatch_bwd_raw(int act, int nx, int nt, const BwdArgs& a, int grid, cudaStream_t s) {
 #define CASE(X_, T_)                                                        \
     if (nx == X_ && nt == T_) {                                             \
         switch (act) {                                                      \
@@ -255,6 +264,17 @@ static int dispatch_bwd(int act, int nx, int nt, const BwdArgs& a, int grid, cud
     PDR_BWD_COMBOS(CASE)
 #undef CASE
     return PDEREAD_ERR_UNSUPPORTED_ORDER;
+}
+
+static int dispatch_fwd(int act, int nx, int nt, const FwdArgs& a, cudaStream_t s) {
+    const int rc = dispatch_fwd_raw(act, nx, nt, a, s);
+    if (rc == PDEREAD_OK) stage_mark(s);
+    return rc;
+}
+static int dispatch_bwd(int act, int nx, int nt, const BwdArgs& a, int grid, cudaStream_t s) {
+    const int rc = dispatch_bwd_raw(act, nx, nt, a, grid, s);
+    if (rc == PDEREAD_OK) stage_mark(s);
+    return rc;
 }
 
 static int check_smem(int W, int L, int din, int J, bool bwd) {
@@ -308,6 +328,7 @@ static int pack(const NetDev& n, float* wt, float* wn, cudaStream_t s) {
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
     pack_weights_kernel<<<blocks, 256, 0, s>>>(n, wt, wn);
     PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark(s);
     return PDEREAD_OK;
 }
 
@@ -316,6 +337,7 @@ static int reduce_partials(const float* gpart, int nparts, const GradLayout& lay
     const int blocks = (lay.total + 127) / 128;
     reduce_partials_kernel<<<blocks, 128, 0, s>>>(gpart, nparts, lay.total, tab, beta, scale);
     PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark(s);
     return PDEREAD_OK;
 }
 
@@ -346,6 +368,14 @@ const char* pderead_status_string(int status) {
 }
 
 int pderead_last_cuda_error(void) { return g_last_cuda_error; }
+
+int pderead_debug_stage_events(void* const* events, int count) {
+    g_stage_events = (cudaEvent_t*)events;
+    g_stage_count = events ? count : 0;
+    g_stage_next = 0;
+    return PDEREAD_OK;
+}
+int pderead_debug_stage_events_recorded(void) { return g_stage_next; }
 
 // ------------------------------------------------------------------------------------------
 // Evaluate_Derivatives

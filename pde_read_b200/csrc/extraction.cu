@@ -234,6 +234,7 @@ int gram_launch(const LibTable& t, bool dense, const float* src, const float* b,
         gram_kernel<false><<<grid, 256, smem, s>>>(t, src, b, M, nblk, G, Atb, btb);
     }
     PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark(s);
     return PDEREAD_OK;
 }
 
@@ -450,6 +451,7 @@ int pderead_rfe_gram(const double* d_G, const double* d_Atb, const double* d_btb
     rfe_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(d_G, d_Atb, d_btb, C, d_X, d_residual, d_order, d_rank, d_change,
                                                         (double*)ws, use_smem);
     PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark((cudaStream_t)stream);
     return PDEREAD_OK;
 }
 

@@ -103,6 +103,7 @@ size_t bwd_smem_bytes(int W, int L, int din, int J);
 int block_warps(int W);
 
 void set_last_cuda_error(cudaError_t e);
+void stage_mark(cudaStream_t s);   // measurement hook, see pderead_debug_stage_events
 
 // extraction.cu
 int library_gram_launch(const float* dxn, const float* b, long long M, int n, int K, double* G, double* Atb,
