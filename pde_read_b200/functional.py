@@ -378,7 +378,8 @@ class CollocationLossFn(torch.autograd.Function):
                                                         M_total=M_total, extra_tail=4 if reducer is not None else 0)
             if reducer is not None:
                 ss = reducer.reduce(flat, ss)
-            ctx.save_for_backward(*vu, *vn)
+            ctx.save_for_backward(flat)
+            ctx.shapes = [tuple(t.shape) for t in tensors]
         else:
             _, ss = residual_forward(sol_spec, sol_t, pde_spec, pde_t, m, n, coords, want_resid=False)
             if reducer is not None:
@@ -390,8 +391,17 @@ class CollocationLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        grads = [(v * g if f else None) for v, f in zip(ctx.saved_tensors, ctx.flags)] if ctx.need_grad else \
-                [None] * len(ctx.flags)
+        if not ctx.need_grad:
+            return (None,) * (7 + len(ctx.flags))
+        (flat,) = ctx.saved_tensors
+        scaled = flat * g          # one launch for all parameter tensors
+        grads, off = [], 0
+        for shape, f in zip(ctx.shapes, ctx.flags):
+            numel = 1
+            for d in shape:
+                numel *= d
+            grads.append(scaled[off:off + numel].view(shape) if f else None)
+            off += (numel + 3) // 4 * 4
         return (None, None, None, None, None, None, None, *grads)
 
 
