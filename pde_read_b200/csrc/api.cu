@@ -3,7 +3,10 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "internal.h"
+#include "umma.cuh"
 
 namespace pdr {
 
@@ -70,6 +73,44 @@ __global__ void reduce_partials_kernel(const float* __restrict__ gpart, int npar
         for (int p = 0; p < nparts; ++p) acc += gpart[(size_t)p * stride + e];
         float* d = tab.seg[s].dst + (e - tab.seg[s].off);
         *d = (beta == 0.f ? 0.f : beta * (*d)) + scale * acc;
+    }
+}
+
+// ---- weight images ------------------------------------------------------------------------------
+// One image per product gi = 1..L of a network: [hi | lo], each MROWS x Kpad fp32, K-major core-matrix
+// layout (8 rows x 16 bytes contiguous; LBO = 128 between 4-k groups, SBO = a_rs between 8-row groups).
+// Row r of image gi < L holds the weights of neuron nid(r) of hidden layer gi (zero for unused rows);
+// image L holds the output layer's weights in row 0.  transpose != 0 packs W^T (for hbar = W^T zbar).
+__global__ void tc_pack_weights_kernel(NetDev net, int mrows, int Kpad, int NB, int a_rs, int a_bytes, int transpose,
+                                       float* __restrict__ img) {
+    const int W = net.W, L = net.L;
+    const size_t per_img = (size_t)2 * a_bytes / 4;   // floats
+    const int per_mat = mrows * Kpad;
+    const int nimg = L;   // forward: L-1 hidden + output row; transposed: L-1 hidden + input layer (for the input gradient)
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)nimg * per_mat;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int gi = (int)(idx / per_mat) + 1;
+        const int rem = (int)(idx - (size_t)(gi - 1) * per_mat);
+        const int r = rem / Kpad, k = rem - r * Kpad;
+        const int blk = (mrows == 64) ? 16 : 32;
+        const int qd = r / blk, rl = r - qd * blk;
+        const int nid = qd * NB + rl;
+        float v = 0.f;
+        if (k < W) {
+            if (gi < L) {
+                if (rl < NB && nid < W) v = transpose ? net.w[gi][(size_t)k * W + nid] : net.w[gi][(size_t)nid * W + k];
+            } else if (!transpose) {
+                if (r == 0) v = net.w[L][k];
+            } else {
+                if (r < net.din) v = net.w[0][(size_t)k * net.din + r];
+            }
+        }
+        const size_t off = ((size_t)(r & 7) * 16 + (size_t)(r >> 3) * a_rs + (size_t)(k & 3) * 4 + (size_t)(k >> 2) * 128) / 4;
+        float hi, lo;
+        umma::tf32_split(v, hi, lo);
+        float* base = img + (size_t)(gi - 1) * per_img;
+        base[off] = hi;
+        base[(size_t)a_bytes / 4 + off] = lo;
     }
 }
 
@@ -221,6 +262,168 @@ static bool order_supported(int nx, int nt) {
     return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// tensor-core path: geometry, weight images, dispatch
+// ---------------------------------------------------------------------------------------------
+// Tensor-core policy.  0 = off: CUDA-core kernels everywhere.  1 = auto (default): forward-only calls of
+// networks wider than 64 run on the tensor cores (measured 1.6-2x faster there, and inside the stated
+// derivative / residual tolerances); everything on the gradient path stays on the CUDA cores, because the
+// tensor core truncates inside its accumulation and 3xTF32 lands at ~1e-6 relative error per network
+// instead of fp32's ~1e-7, which the residual cancellation of a trained network amplifies in the
+// gradients.  2 = force: tensor cores wherever the shape is supported.
+static int g_tc_mode = -1;
+static int tc_mode() {
+    if (g_tc_mode < 0) {
+        const char* e = getenv("PDEREAD_TC");
+        g_tc_mode = 1;
+        if (e && (e[0] == 'o' || e[0] == 'O' || e[0] == '0')) g_tc_mode = 0;
+        if (e && (e[0] == 'f' || e[0] == 'F' || e[0] == '2')) g_tc_mode = 2;
+    }
+    return g_tc_mode;
+}
+static bool tc_allowed(const NetDev& n, bool gradient_path) {
+    const int m = tc_mode();
+    if (m == 0) return false;
+    if (m == 2) return true;
+    return !gradient_path && n.W > 64;
+}
+
+static int round_up_i(int v, int a) { return (v + a - 1) / a * a; }
+
+// Picks the tile geometry of the tensor-core kernels for one network and jet length; false if the
+// shape is not supported (then the CUDA-core kernels run).
+static bool tc_geometry(const NetDev& n, int J, bool gradient_path, TcGeom* g) {
+    if (!tc_allowed(n, gradient_path)) return false;
+    if (n.L < 2 || n.W < 8 || n.W > 128 || J < 1 || J > 7) return false;
+    int dev = 0, maxsm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
+    memset(g, 0, sizeof(*g));
+    g->mrows = (n.W <= 64) ? 64 : 128;
+    const int subs = (g->mrows == 64) ? 2 : 1;
+    g->Kpad = round_up_i(n.W, 8);
+    g->NB = (n.W + 3) / 4;
+    g->a_rs = (g->Kpad / 4) * 128;
+    g->a_bytes = (g->mrows / 8) * g->a_rs;
+    g->b_rs = (g->Kpad / 4) * 144;
+    const int pcs_jet[] = {16, 8, 4, 0}, pcs_plain[] = {64, 32, 16, 8, 0};
+    const int* pcs = (J == 1) ? pcs_plain : pcs_jet;
+    for (int nwbuf = 2; nwbuf >= 1; --nwbuf) {
+        for (int t = 0; pcs[t]; ++t) {
+            const int PC = pcs[t];
+            if ((PC / 2) % (J <= 4 ? 4 : 2) != 0) continue;   // the epilogue loads G points per TMEM access
+            const int ncpad = round_up_i(PC * J, g->mrows == 128 ? 16 : 8);
+            if (ncpad > 128) continue;
+            const int slot = (ncpad / 8) * g->b_rs;
+            const int sub_stride = 4 * slot + 64;
+            const int TP = subs * 2 * PC;
+            const size_t smem = (size_t)nwbuf * 2 * g->a_bytes + (size_t)subs * sub_stride +
+                                (size_t)((n.din * TP + 1) & ~1) * 4 + 9 * 8 + 64;
+            if (smem > (size_t)maxsm) continue;
+            // prefer the larger chunk; with one weight buffer only if two do not fit at any chunk size >= 8
+            if (nwbuf == 2 && PC < 8 && J > 1) continue;
+            g->PC = PC;
+            g->NCpad = ncpad;
+            g->TP = TP;
+            g->slot_bytes = slot;
+            g->sub_stride = sub_stride;
+            g->nwbuf = nwbuf;
+            int cols = 32;
+            while (cols < 4 * ncpad) cols <<= 1;     // 2 chunks x (main + correction accumulators)
+            g->tmem_cols = cols;
+            g->smem_bytes = smem;
+            return true;
+        }
+    }
+    return false;
+}
+
+// upper bound of the weight-image bytes of one network (L products, hi|lo, M = 128 rows)
+static size_t tc_image_bytes_bound(const NetDev& n) {
+    if (n.W > 128 || n.L < 2) return 0;
+    return (size_t)n.L * 2 * 16 * (size_t)(round_up_i(n.W, 8) / 4) * 128;
+}
+
+static int tc_pack(const NetDev& n, int mrows, int Kpad, int NB, int a_rs, int a_bytes, int transpose, float* img,
+                   cudaStream_t s) {
+    const size_t total = (size_t)n.L * mrows * Kpad;
+    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    tc_pack_weights_kernel<<<blocks, 256, 0, s>>>(n, mrows, Kpad, NB, a_rs, a_bytes, transpose, img);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark(s);
+    return PDEREAD_OK;
+}
+
+static int jet_cols(int J) { return (J == 3) ? 4 : (J == 5) ? 6 : (J == 7) ? 8 : J; }
+
+// Geometry of the tensor-core reverse kernel; false -> CUDA-core kernels.
+static bool tc_bwd_geometry(const NetDev& n, int J, bool want_gin, TcBwdGeom* g) {
+    if (!tc_allowed(n, true)) return false;
+    if (n.L < 2 || n.W < 8 || n.W > 128 || J < 1 || J > 7) return false;
+    if (want_gin && J != 1) return false;
+    int dev = 0, maxsm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
+    memset(g, 0, sizeof(*g));
+    g->mrows = (n.W <= 64) ? 64 : 128;
+    const int subs = (g->mrows == 64) ? 2 : 1;
+    const int gran = (g->mrows == 128) ? 16 : 8;
+    g->Kpad = round_up_i(n.W, 8);
+    g->NB = (n.W + 3) / 4;
+    g->Jp = jet_cols(J);
+    const int G = (g->Jp == 1) ? 8 : (g->Jp == 2) ? 4 : 2;
+    g->a_rs = (g->Kpad / 4) * 128;
+    g->a_bytes = (g->mrows / 8) * g->a_rs;
+    g->zt_rs = (g->Kpad / 4) * 144;
+    g->npad_w = round_up_i(g->Kpad, gran);
+    const int NS = n.L * n.W + 1 + n.W * n.din + n.W + 7 * n.L;
+    const int pcs_jet[] = {16, 8, 4, 0}, pcs_plain[] = {64, 32, 16, 0};
+    const int* pcs = (J == 1) ? pcs_plain : pcs_jet;
+    for (int nchunk = 2; nchunk >= 1; --nchunk) {
+        for (int t = 0; pcs[t]; ++t) {
+            for (int nwbuf = 2; nwbuf >= 1; --nwbuf) {
+                const int PC = pcs[t];
+                if ((PC / 2) % G != 0) continue;
+                const int NC = PC * g->Jp;
+                if (NC % 8 != 0) continue;
+                const int ncpad = round_up_i(NC, gran);
+                if (ncpad > 256) continue;
+                const int tmem = 2 * nchunk * ncpad + (n.L - 1) * g->npad_w;   // hbar: main + correction accumulators
+                if (tmem > 512) continue;
+                const int za_rs = (NC / 4) * 128;
+                const int za_bytes = (g->mrows / 8) * za_rs, yb_bytes = (g->npad_w / 8) * za_rs;
+                const int zt_bytes = (ncpad / 8) * g->zt_rs;
+                const int set_bytes = 2 * (zt_bytes + za_bytes + yb_bytes);
+                const int sub_stride = nchunk * set_bytes + 64;
+                const int TP = subs * nchunk * PC;
+                const size_t smem = (size_t)nwbuf * 2 * g->a_bytes + (size_t)subs * sub_stride +
+                                    (size_t)(n.din * TP + J * TP + ((NS + 1) & ~1)) * 4 + 9 * 8 + 64;
+                if (smem > (size_t)maxsm) continue;
+                g->PC = PC;
+                g->nchunk = nchunk;
+                g->NC = NC;
+                g->NCpad = ncpad;
+                g->TP = TP;
+                g->zt_bytes = zt_bytes;
+                g->za_bytes = za_bytes;
+                g->za_rs = za_rs;
+                g->yb_bytes = yb_bytes;
+                g->set_bytes = set_bytes;
+                g->sub_stride = sub_stride;
+                g->nwbuf = nwbuf;
+                g->gcol0 = 2 * nchunk * ncpad;
+                int cols = 32;
+                while (cols < tmem) cols <<= 1;
+                g->tmem_cols = cols;
+                g->smem_bytes = smem;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
 #define PDR_FWD_COMBOS(X) X(0, 0) X(1, 0) X(2, 0) X(3, 0) X(4, 0) X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(1, 2) X(2, 2) X(3, 2) X(4, 2)
 #define PDR_BWD_COMBOS(X) X(0, 0) X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(1, 2) X(2, 2) X(3, 2) X(4, 2)
 
@@ -321,6 +524,11 @@ struct Carver {
 
 static size_t packed_floats(const NetDev& n) { return (size_t)(n.L > 1 ? n.L - 1 : 0) * n.W * n.NC * TNP; }
 static size_t stash_floats_per_point(const NetDev& n, int J) { return (size_t)(n.L > 1 ? n.L - 1 : 0) * n.W * J; }
+// bound for the workspace queries: the tensor-core stash keeps 64 / 128 rows per layer
+static size_t stash_floats_bound(const NetDev& n, int J) {
+    const size_t rows = (n.W <= 64) ? 64 : (n.W <= 128 ? 128 : (size_t)n.W);
+    return (size_t)(n.L > 1 ? n.L - 1 : 0) * rows * J;
+}
 
 static int pack(const NetDev& n, float* wt, float* wn, cudaStream_t s) {
     if (n.L <= 1 || (!wt && !wn)) return PDEREAD_OK;
@@ -339,6 +547,87 @@ static int reduce_partials(const float* gpart, int nparts, const GradLayout& lay
     PDR_CUDA_CHECK(cudaGetLastError());
     stage_mark(s);
     return PDEREAD_OK;
+}
+
+
+static int dispatch_tc_fwd(int act, int nx, int nt, const TcFwdArgs& a, cudaStream_t s) {
+#define CASE(X_, T_)                                                   \
+    if (nx == X_ && nt == T_) {                                        \
+        switch (act) {                                                 \
+            case 0: { const int rc = launch_tc_fwd<0, X_, T_>(a, s); if (rc == PDEREAD_OK) stage_mark(s); return rc; } \
+            case 1: { const int rc = launch_tc_fwd<1, X_, T_>(a, s); if (rc == PDEREAD_OK) stage_mark(s); return rc; } \
+            case 2: { const int rc = launch_tc_fwd<2, X_, T_>(a, s); if (rc == PDEREAD_OK) stage_mark(s); return rc; } \
+        }                                                              \
+    }
+    PDR_FWD_COMBOS(CASE)
+#undef CASE
+    return PDEREAD_ERR_UNSUPPORTED_ORDER;
+}
+
+static int dispatch_tc_bwd(int act, int nx, int nt, const TcBwdArgs& a, int grid, cudaStream_t s) {
+#define CASE(X_, T_)                                                   \
+    if (nx == X_ && nt == T_) {                                        \
+        switch (act) {                                                 \
+            case 0: { const int rc = launch_tc_bwd<0, X_, T_>(a, grid, s); if (rc == PDEREAD_OK) stage_mark(s); return rc; } \
+            case 1: { const int rc = launch_tc_bwd<1, X_, T_>(a, grid, s); if (rc == PDEREAD_OK) stage_mark(s); return rc; } \
+            case 2: { const int rc = launch_tc_bwd<2, X_, T_>(a, grid, s); if (rc == PDEREAD_OK) stage_mark(s); return rc; } \
+        }                                                              \
+    }
+    PDR_BWD_COMBOS(CASE)
+#undef CASE
+    return PDEREAD_ERR_UNSUPPORTED_ORDER;
+}
+
+// A forward launch of one network on whichever path its plan selected.
+struct FwdPlan {
+    bool tc;
+    TcGeom geom;
+    float* wt;    // CUDA-core path: packed transposed weights
+    float* img;   // tensor-core path: weight images
+};
+
+static int plan_forward(const NetDev& n, int J, bool allow_tc, Carver& cv, FwdPlan* p) {
+    memset(p, 0, sizeof(*p));
+    p->tc = allow_tc && tc_geometry(n, J, false, &p->geom);
+    if (p->tc) {
+        p->img = cv.take<float>((size_t)n.L * 2 * p->geom.a_bytes / 4);
+    } else {
+        p->wt = cv.take<float>(packed_floats(n));
+    }
+    return cv.ok ? PDEREAD_OK : PDEREAD_ERR_WORKSPACE_TOO_SMALL;
+}
+
+static int plan_pack(const NetDev& n, const FwdPlan& p, cudaStream_t s) {
+    if (p.tc) return tc_pack(n, p.geom.mrows, p.geom.Kpad, p.geom.NB, p.geom.a_rs, p.geom.a_bytes, 0, p.img, s);
+    return pack(n, p.wt, nullptr, s);
+}
+
+// `f` carries everything except wt_packed / num_tiles, which depend on the path.
+static int plan_launch(int act, int nx, int nt, const FwdPlan& p, FwdArgs f, cudaStream_t s) {
+    if (!p.tc) {
+        const int TP = tile_points(jet_len(nx, nt));
+        f.wt_packed = p.wt;
+        f.num_tiles = (f.M + TP - 1) / TP;
+        return dispatch_fwd(act, nx, nt, f, s);
+    }
+    TcFwdArgs t;
+    memset(&t, 0, sizeof(t));
+    t.net = f.net;
+    t.geom = p.geom;
+    t.wimg = p.img;
+    t.in = f.in;
+    t.M = f.M;
+    t.num_tiles = (f.M + p.geom.TP - 1) / p.geom.TP;
+    t.out0 = f.out0;
+    t.out1 = f.out1;
+    t.stash = f.stash;
+    t.dtm_in = f.dtm_in;
+    t.resid_out = f.resid_out;
+    t.seed_out = f.seed_out;
+    t.grad_resid = f.grad_resid;
+    t.seed_scale = f.seed_scale;
+    t.sumsq = f.sumsq;
+    return dispatch_tc_fwd(act, nx, nt, t, s);
 }
 
 constexpr long long CHUNK_ALIGN = 128;          // lcm of all tile sizes
@@ -377,6 +666,12 @@ int pderead_debug_stage_events(void* const* events, int count) {
 }
 int pderead_debug_stage_events_recorded(void) { return g_stage_next; }
 
+int pderead_debug_set_tensor_cores(int mode) {
+    const int prev = tc_mode();
+    g_tc_mode = (mode < 0 || mode > 2) ? 1 : mode;
+    return prev;
+}
+
 // ------------------------------------------------------------------------------------------
 // Evaluate_Derivatives
 // ------------------------------------------------------------------------------------------
@@ -385,11 +680,12 @@ size_t pderead_sol_derivatives_workspace_bytes(const pderead_net* sol, int m, in
     if (to_netdev(sol, &U) != PDEREAD_OK || M < 0) return 0;
     const int J = jet_len(n, m);
     size_t bytes = align_up(packed_floats(U) * 4, 256) * (need_backward ? 2 : 1);
+    bytes += align_up(tc_image_bytes_bound(U), 256) * (need_backward ? 2 : 1);
     if (need_backward) {
         const GradLayout lay = make_layout(U);
         bytes += align_up((size_t)max_grid(U, J) * lay.total * 4, 256);
         const long long chunk = round_up_ll(M < CHUNK_TARGET ? (M > 0 ? M : 1) : CHUNK_TARGET, CHUNK_ALIGN);
-        bytes += align_up((size_t)chunk * stash_floats_per_point(U, J) * 4, 256);
+        bytes += align_up((size_t)chunk * stash_floats_bound(U, J) * 4, 256);
         bytes += align_up((size_t)chunk * (n + 2) * 4, 256) * 2;
     }
     return bytes + 1024;
@@ -405,22 +701,113 @@ int pderead_sol_derivatives_forward(const pderead_net* sol, int m, int n, const 
     if (M < 0 || (M > 0 && (!d_coords || !d_dxn))) return PDEREAD_ERR_BAD_ARGUMENT;
     if (M == 0) return PDEREAD_OK;
     const int J = jet_len(n, m);
-    if ((rc = check_smem(U.W, U.L, U.din, J, false))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     Carver cv(ws, ws_bytes);
-    float* wt = cv.take<float>(packed_floats(U));
-    if (!cv.ok || (packed_floats(U) && !ws)) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
-    if ((rc = pack(U, wt, nullptr, s))) return rc;
+    FwdPlan pl;
+    if ((rc = plan_forward(U, J, true, cv, &pl))) return rc;
+    if (!pl.tc && (rc = check_smem(U.W, U.L, U.din, J, false))) return rc;
+    if (!ws && (pl.tc || packed_floats(U))) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
+    if ((rc = plan_pack(U, pl, s))) return rc;
     FwdArgs a;
     memset(&a, 0, sizeof(a));
     a.net = U;
-    a.wt_packed = wt;
     a.in = d_coords;
     a.M = M;
-    a.num_tiles = (M + tile_points(J) - 1) / tile_points(J);
     a.out0 = d_dxn;
     a.out1 = d_dtm;
-    return dispatch_fwd(sol->activation, n, m, a, s);
+    return plan_launch(sol->activation, n, m, pl, a, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reverse-pass plan of one network: tensor-core kernels (forward with stash + reverse) when the shape
+// is supported, the CUDA-core kernels otherwise
+// ---------------------------------------------------------------------------------------------
+struct BwdPlan {
+    bool tc;
+    FwdPlan fwd;
+    TcBwdGeom bgeom;
+    float* wn;      // CUDA-core path: native packed weights
+    float* timg;    // tensor-core path: transposed weight images
+    int grid;       // CTAs of the reverse kernel = number of partial-gradient vectors
+    float* gpart;
+    size_t stash_pp;   // stash floats per point
+};
+
+static int plan_backward(const NetDev& n, int act, int nx, int nt, bool want_gin, int64_t M, const GradLayout& lay,
+                         Carver& cv, BwdPlan* p) {
+    int rc;
+    const int J = jet_len(nx, nt);
+    memset(p, 0, sizeof(*p));
+    p->tc = tc_geometry(n, J, true, &p->fwd.geom) && tc_bwd_geometry(n, J, want_gin, &p->bgeom);
+    p->fwd.tc = p->tc;
+    if (p->tc) {
+        int dev = 0, sms = 0;
+        PDR_CUDA_CHECK(cudaGetDevice(&dev));
+        PDR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        p->fwd.img = cv.take<float>((size_t)n.L * 2 * p->fwd.geom.a_bytes / 4);
+        p->timg = cv.take<float>((size_t)n.L * 2 * p->bgeom.a_bytes / 4);
+        const long long tiles = (M + p->bgeom.TP - 1) / p->bgeom.TP;
+        p->grid = (int)(tiles < sms ? tiles : sms);
+        p->stash_pp = (size_t)(n.L - 1) * J * p->bgeom.mrows;
+    } else {
+        if ((rc = check_smem(n.W, n.L, n.din, J, true))) return rc;
+        if ((rc = check_smem(n.W, n.L, n.din, J, false))) return rc;
+        p->fwd.wt = cv.take<float>(packed_floats(n));
+        p->wn = cv.take<float>(packed_floats(n));
+        const int TP = tile_points(J);
+        if ((rc = dispatch_bwd_grid(act, nx, nt, n.W, n.L, n.din, (M + TP - 1) / TP, &p->grid))) return rc;
+        p->stash_pp = stash_floats_per_point(n, J);
+    }
+    p->gpart = cv.take<float>((size_t)p->grid * lay.total);
+    return cv.ok ? PDEREAD_OK : PDEREAD_ERR_WORKSPACE_TOO_SMALL;
+}
+
+static int plan_backward_pack(const NetDev& n, const BwdPlan& p, cudaStream_t s) {
+    int rc;
+    if (p.tc) {
+        const TcGeom& f = p.fwd.geom;
+        if ((rc = tc_pack(n, f.mrows, f.Kpad, f.NB, f.a_rs, f.a_bytes, 0, p.fwd.img, s))) return rc;
+        const TcBwdGeom& b = p.bgeom;
+        return tc_pack(n, b.mrows, b.Kpad, b.NB, b.a_rs, b.a_bytes, 1, p.timg, s);
+    }
+    return pack(n, p.fwd.wt, p.wn, s);
+}
+
+// `b` carries everything except the packed weights / tiles / grid, which depend on the path.
+static int plan_backward_launch(int act, int nx, int nt, BwdPlan& p, BwdArgs b, bool first, cudaStream_t s) {
+    b.accumulate = first ? 0 : 1;
+    b.gpart = p.gpart;
+    if (p.tc) {
+        TcBwdArgs t;
+        memset(&t, 0, sizeof(t));
+        t.net = b.net;
+        t.lay = b.lay;
+        t.geom = p.bgeom;
+        t.wimg = p.timg;
+        t.in = b.in;
+        t.M = b.M;
+        t.num_tiles = (b.M + p.bgeom.TP - 1) / p.bgeom.TP;
+        t.stash = b.stash;
+        t.g0 = b.g0;
+        t.g1 = b.g1;
+        t.g0_scale = b.g0_scale;
+        t.g1_scale = b.g1_scale;
+        t.gin = b.gin;
+        t.gpart = p.gpart;
+        t.accumulate = b.accumulate;
+        int g = p.grid;
+        if (t.num_tiles < g) g = (int)t.num_tiles;
+        if (first) p.grid = g;      // later chunks are never larger than the first
+        return dispatch_tc_bwd(act, nx, nt, t, g, s);
+    }
+    const int TP = tile_points(jet_len(nx, nt));
+    b.wn_packed = p.wn;
+    b.num_tiles = (b.M + TP - 1) / TP;
+    b.wg_mode = (b.net.W == 50) ? 1 : 0;
+    int g = p.grid;
+    if (b.num_tiles < g) g = (int)b.num_tiles;
+    if (first) p.grid = g;
+    return dispatch_bwd(act, nx, nt, b, g, s);
 }
 
 // shared implementation of "forward with stash + backward" over chunks for one network
@@ -429,79 +816,56 @@ static int net_backward_chunked(const NetDev& net, int act, int nx, int nt, cons
                                 float beta, void* ws, size_t ws_bytes, cudaStream_t s) {
     int rc;
     const int J = jet_len(nx, nt);
-    if ((rc = check_smem(net.W, net.L, net.din, J, true))) return rc;
-    if ((rc = check_smem(net.W, net.L, net.din, J, false))) return rc;
     const GradLayout lay = make_layout(net);
     SegmentTable tab;
     if ((rc = make_segments(net, act, lay, grads, &tab))) return rc;
-    const int TP = tile_points(J);
 
     Carver cv(ws, ws_bytes);
-    float* wt = cv.take<float>(packed_floats(net));
-    float* wn = cv.take<float>(packed_floats(net));
-    // grid for the largest chunk we might run
-    int grid = 0;
-    const long long tiles_all = (M + TP - 1) / TP;
-    if ((rc = dispatch_bwd_grid(act, nx, nt, net.W, net.L, net.din, tiles_all, &grid))) return rc;
-    float* gpart = cv.take<float>((size_t)grid * lay.total);
-    if (!cv.ok) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
+    BwdPlan pl;
+    if ((rc = plan_backward(net, act, nx, nt, d_gin != nullptr, M, lay, cv, &pl))) return rc;
     // remaining bytes decide the chunk size
-    const size_t per_point = (stash_floats_per_point(net, J) + (size_t)(nx + 2)) * 4;
+    const size_t per_point = (pl.stash_pp + (size_t)(nx + 2)) * 4;
     const size_t remain = ws_bytes - cv.used;
     long long chunk = (long long)((remain > 4096 ? remain - 4096 : 0) / (per_point ? per_point : 1));
     chunk = chunk / CHUNK_ALIGN * CHUNK_ALIGN;
     if (chunk < CHUNK_ALIGN) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
     if (chunk > round_up_ll(M, CHUNK_ALIGN)) chunk = round_up_ll(M, CHUNK_ALIGN);
-    float* stash = cv.take<float>((size_t)chunk * stash_floats_per_point(net, J));
+    float* stash = cv.take<float>((size_t)chunk * pl.stash_pp);
     float* scratch0 = cv.take<float>((size_t)chunk * (nx + 1));
     float* scratch1 = cv.take<float>((size_t)chunk);
     if (!cv.ok) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
-    if ((rc = pack(net, wt, wn, s))) return rc;
+    if ((rc = plan_backward_pack(net, pl, s))) return rc;
 
     bool first = true;
     for (int64_t lo = 0; lo < M; lo += chunk) {
         const int64_t mc = (M - lo < chunk) ? (M - lo) : chunk;
-        const long long tiles = (mc + TP - 1) / TP;
         if (net.L > 1) {
             FwdArgs f;
             memset(&f, 0, sizeof(f));
             f.net = net;
-            f.wt_packed = wt;
             f.in = d_in + lo * net.din;
             f.M = mc;
-            f.num_tiles = tiles;
             f.out0 = scratch0;
             f.out1 = scratch1;
             f.stash = stash;
-            if ((rc = dispatch_fwd(act, nx, nt, f, s))) return rc;
+            if ((rc = plan_launch(act, nx, nt, pl.fwd, f, s))) return rc;
         }
         BwdArgs b;
         memset(&b, 0, sizeof(b));
         b.net = net;
         b.lay = lay;
-        b.wn_packed = wn;
         b.in = d_in + lo * net.din;
         b.M = mc;
-        b.num_tiles = tiles;
         b.stash = stash;
         b.g0 = g0 ? g0 + lo * (J == 1 ? 1 : (nx + 1)) : nullptr;
         b.g1 = g1 ? g1 + lo : nullptr;
         b.g0_scale = 1.f;
         b.g1_scale = 1.f;
         b.gin = d_gin ? d_gin + lo * net.din : nullptr;
-        b.gpart = gpart;
-        b.wg_mode = (net.W == 50) ? 1 : 0;
-        b.accumulate = first ? 0 : 1;
-        int g = grid;
-        if (tiles < g) g = (int)tiles;
-        if (first && g < grid) {
-            // later chunks are never larger than the first, so `g` partial vectors is all we sum
-            grid = g;
-        }
-        if ((rc = dispatch_bwd(act, nx, nt, b, g, s))) return rc;
+        if ((rc = plan_backward_launch(act, nx, nt, pl, b, first, s))) return rc;
         first = false;
     }
-    return reduce_partials(gpart, grid, lay, tab, beta, 1.f, s);
+    return reduce_partials(pl.gpart, pl.grid, lay, tab, beta, 1.f, s);
 }
 
 int pderead_sol_derivatives_backward(const pderead_net* sol, int m, int n, const float* d_coords, int64_t M,
@@ -524,11 +888,12 @@ size_t pderead_mlp_workspace_bytes(const pderead_net* net, int64_t M, int need_b
     NetDev N;
     if (to_netdev(net, &N) != PDEREAD_OK || M < 0) return 0;
     size_t bytes = align_up(packed_floats(N) * 4, 256) * (need_backward ? 2 : 1);
+    bytes += align_up(tc_image_bytes_bound(N), 256) * (need_backward ? 2 : 1);
     if (need_backward) {
         const GradLayout lay = make_layout(N);
         bytes += align_up((size_t)max_grid(N, 1) * lay.total * 4, 256);
         const long long chunk = round_up_ll(M < CHUNK_TARGET ? (M > 0 ? M : 1) : CHUNK_TARGET, CHUNK_ALIGN);
-        bytes += align_up((size_t)chunk * stash_floats_per_point(N, 1) * 4, 256);
+        bytes += align_up((size_t)chunk * stash_floats_bound(N, 1) * 4, 256);
         bytes += align_up((size_t)chunk * 2 * 4, 256) * 2;
     }
     return bytes + 8192;
@@ -541,21 +906,20 @@ int pderead_mlp_forward(const pderead_net* net, const float* d_in, int64_t M, fl
     if (rc) return rc;
     if (M < 0 || (M > 0 && (!d_in || !d_out))) return PDEREAD_ERR_BAD_ARGUMENT;
     if (M == 0) return PDEREAD_OK;
-    if ((rc = check_smem(N.W, N.L, N.din, 1, false))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     Carver cv(ws, ws_bytes);
-    float* wt = cv.take<float>(packed_floats(N));
-    if (!cv.ok || (packed_floats(N) && !ws)) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
-    if ((rc = pack(N, wt, nullptr, s))) return rc;
+    FwdPlan pl;
+    if ((rc = plan_forward(N, 1, true, cv, &pl))) return rc;
+    if (!pl.tc && (rc = check_smem(N.W, N.L, N.din, 1, false))) return rc;
+    if (!ws && (pl.tc || packed_floats(N))) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
+    if ((rc = plan_pack(N, pl, s))) return rc;
     FwdArgs a;
     memset(&a, 0, sizeof(a));
     a.net = N;
-    a.wt_packed = wt;
     a.in = d_in;
     a.M = M;
-    a.num_tiles = (M + tile_points(1) - 1) / tile_points(1);
     a.out0 = d_out;
-    return dispatch_fwd(net->activation, 0, 0, a, s);
+    return plan_launch(net->activation, 0, 0, pl, a, s);
 }
 
 int pderead_mlp_backward(const pderead_net* net, const float* d_in, int64_t M, const float* d_grad_out,
@@ -581,12 +945,13 @@ size_t pderead_residual_workspace_bytes(const pderead_net* sol, const pderead_ne
     size_t bytes = 0;
     bytes += align_up(packed_floats(U) * 4, 256) * (need_backward ? 2 : 1);
     bytes += align_up(packed_floats(N) * 4, 256) * (need_backward ? 2 : 1);
+    bytes += (align_up(tc_image_bytes_bound(U), 256) + align_up(tc_image_bytes_bound(N), 256)) * (need_backward ? 2 : 1);
     bytes += align_up((size_t)chunk * (n + 1) * 4, 256) + align_up((size_t)chunk * 4, 256);   // dxn, dtm
     if (need_backward) {
         const GradLayout lu = make_layout(U), ln = make_layout(N);
         bytes += align_up((size_t)max_grid(U, J) * lu.total * 4, 256) + align_up((size_t)max_grid(N, 1) * ln.total * 4, 256);
-        bytes += align_up((size_t)chunk * stash_floats_per_point(U, J) * 4, 256);
-        bytes += align_up((size_t)chunk * stash_floats_per_point(N, 1) * 4, 256);
+        bytes += align_up((size_t)chunk * stash_floats_bound(U, J) * 4, 256);
+        bytes += align_up((size_t)chunk * stash_floats_bound(N, 1) * 4, 256);
         bytes += align_up((size_t)chunk * (n + 1) * 4, 256) + align_up((size_t)chunk * 4, 256);   // gdxn, seedN
     }
     return bytes + 8192;
@@ -604,12 +969,6 @@ static int residual_impl(const pderead_net* sol, const pderead_net* pde, int m, 
     if (U.din != 2 || N.din != n + 1) return PDEREAD_ERR_UNSUPPORTED_NET;
     if (M <= 0 || !d_coords || !ws || M_total < M) return PDEREAD_ERR_BAD_ARGUMENT;
     const int J = jet_len(n, m);
-    const int TPU = tile_points(J), TPN = tile_points(1);
-    if ((rc = check_smem(U.W, U.L, U.din, J, backward))) return rc;
-    if ((rc = check_smem(N.W, N.L, N.din, 1, backward))) return rc;
-    if ((rc = check_smem(U.W, U.L, U.din, J, false))) return rc;
-    if ((rc = check_smem(N.W, N.L, N.din, 1, false))) return rc;
-
     const GradLayout lu = make_layout(U), ln = make_layout(N);
     SegmentTable tu, tn;
     if (backward) {
@@ -618,21 +977,24 @@ static int residual_impl(const pderead_net* sol, const pderead_net* pde, int m, 
     }
 
     Carver cv(ws, ws_bytes);
-    float* wtU = cv.take<float>(packed_floats(U));
-    float* wtN = cv.take<float>(packed_floats(N));
-    float *wnU = nullptr, *wnN = nullptr, *gpU = nullptr, *gpN = nullptr;
-    int gridU = 0, gridN = 0;
+    BwdPlan bU, bN;           // backward: forward-with-stash + reverse plans
+    FwdPlan fU, fN;           // forward only
+    memset(&bU, 0, sizeof(bU));
+    memset(&bN, 0, sizeof(bN));
     if (backward) {
-        wnU = cv.take<float>(packed_floats(U));
-        wnN = cv.take<float>(packed_floats(N));
-        if ((rc = dispatch_bwd_grid(sol->activation, n, m, U.W, U.L, U.din, (M + TPU - 1) / TPU, &gridU))) return rc;
-        if ((rc = dispatch_bwd_grid(pde->activation, 0, 0, N.W, N.L, N.din, (M + TPN - 1) / TPN, &gridN))) return rc;
-        gpU = cv.take<float>((size_t)gridU * lu.total);
-        gpN = cv.take<float>((size_t)gridN * ln.total);
+        if ((rc = plan_backward(U, sol->activation, n, m, false, M, lu, cv, &bU))) return rc;
+        if ((rc = plan_backward(N, pde->activation, 0, 0, true, M, ln, cv, &bN))) return rc;
+        fU = bU.fwd;
+        fN = bN.fwd;
+    } else {
+        if ((rc = plan_forward(U, J, true, cv, &fU))) return rc;
+        if ((rc = plan_forward(N, 1, true, cv, &fN))) return rc;
+        if (!fU.tc && (rc = check_smem(U.W, U.L, U.din, J, false))) return rc;
+        if (!fN.tc && (rc = check_smem(N.W, N.L, N.din, 1, false))) return rc;
     }
     if (!cv.ok) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
     size_t per_point = (size_t)(n + 2) * 4;
-    if (backward) per_point += (stash_floats_per_point(U, J) + stash_floats_per_point(N, 1) + (size_t)(n + 2)) * 4;
+    if (backward) per_point += (bU.stash_pp + bN.stash_pp + (size_t)(n + 2)) * 4;
     const size_t remain = ws_bytes - cv.used;
     long long chunk = (long long)((remain > 8192 ? remain - 8192 : 0) / per_point);
     chunk = chunk / CHUNK_ALIGN * CHUNK_ALIGN;
@@ -642,40 +1004,40 @@ static int residual_impl(const pderead_net* sol, const pderead_net* pde, int m, 
     float* dtm = cv.take<float>((size_t)chunk);
     float *stU = nullptr, *stN = nullptr, *gdxn = nullptr, *seedN = nullptr;
     if (backward) {
-        stU = cv.take<float>((size_t)chunk * stash_floats_per_point(U, J));
-        stN = cv.take<float>((size_t)chunk * stash_floats_per_point(N, 1));
+        stU = cv.take<float>((size_t)chunk * bU.stash_pp);
+        stN = cv.take<float>((size_t)chunk * bN.stash_pp);
         gdxn = cv.take<float>((size_t)chunk * (n + 1));
         seedN = cv.take<float>((size_t)chunk);
     }
     if (!cv.ok) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
 
-    if ((rc = pack(U, wtU, wnU, s))) return rc;
-    if ((rc = pack(N, wtN, wnN, s))) return rc;
+    if (backward) {
+        if ((rc = plan_backward_pack(U, bU, s))) return rc;
+        if ((rc = plan_backward_pack(N, bN, s))) return rc;
+    } else {
+        if ((rc = plan_pack(U, fU, s))) return rc;
+        if ((rc = plan_pack(N, fN, s))) return rc;
+    }
 
     bool first = true;
     for (int64_t lo = 0; lo < M; lo += chunk) {
         const int64_t mc = (M - lo < chunk) ? (M - lo) : chunk;
-        const long long tilesU = (mc + TPU - 1) / TPU, tilesN = (mc + TPN - 1) / TPN;
         // U jets
         FwdArgs fu;
         memset(&fu, 0, sizeof(fu));
         fu.net = U;
-        fu.wt_packed = wtU;
         fu.in = d_coords + lo * 2;
         fu.M = mc;
-        fu.num_tiles = tilesU;
         fu.out0 = dxn;
         fu.out1 = dtm;
         fu.stash = (backward && U.L > 1) ? stU : nullptr;
-        if ((rc = dispatch_fwd(sol->activation, n, m, fu, s))) return rc;
+        if ((rc = plan_launch(sol->activation, n, m, fU, fu, s))) return rc;
         // N forward + residual epilogue
         FwdArgs fn;
         memset(&fn, 0, sizeof(fn));
         fn.net = N;
-        fn.wt_packed = wtN;
         fn.in = dxn;
         fn.M = mc;
-        fn.num_tiles = tilesN;
         fn.stash = (backward && N.L > 1) ? stN : nullptr;
         fn.dtm_in = dtm;
         fn.resid_out = d_resid ? d_resid + lo : nullptr;
@@ -683,54 +1045,38 @@ static int residual_impl(const pderead_net* sol, const pderead_net* pde, int m, 
         fn.grad_resid = d_grad_resid ? d_grad_resid + lo : nullptr;
         fn.seed_scale = (float)(2.0 / (double)M_total);
         fn.sumsq = d_sum_sq;
-        if ((rc = dispatch_fwd(pde->activation, 0, 0, fn, s))) return rc;
+        if ((rc = plan_launch(pde->activation, 0, 0, fN, fn, s))) return rc;
         if (backward) {
             BwdArgs bn;
             memset(&bn, 0, sizeof(bn));
             bn.net = N;
             bn.lay = ln;
-            bn.wn_packed = wnN;
             bn.in = dxn;
             bn.M = mc;
-            bn.num_tiles = tilesN;
             bn.stash = stN;
             bn.g0 = seedN;
             bn.g0_scale = 1.f;
             bn.gin = gdxn;
-            bn.gpart = gpN;
-            bn.wg_mode = (N.W == 50) ? 1 : 0;
-            bn.accumulate = first ? 0 : 1;
-            int gN = gridN;
-            if (tilesN < gN) gN = (int)tilesN;
-            if (first) gridN = gN;
-            if ((rc = dispatch_bwd(pde->activation, 0, 0, bn, gN, s))) return rc;
+            if ((rc = plan_backward_launch(pde->activation, 0, 0, bN, bn, first, s))) return rc;
 
             BwdArgs bu;
             memset(&bu, 0, sizeof(bu));
             bu.net = U;
             bu.lay = lu;
-            bu.wn_packed = wnU;
             bu.in = d_coords + lo * 2;
             bu.M = mc;
-            bu.num_tiles = tilesU;
             bu.stash = stU;
             bu.g0 = gdxn;
             bu.g0_scale = 1.f;
             bu.g1 = seedN;          // dL/dDtm = dL/dR = -dL/dN
             bu.g1_scale = -1.f;
-            bu.gpart = gpU;
-            bu.wg_mode = (U.W == 50) ? 1 : 0;
-            bu.accumulate = first ? 0 : 1;
-            int gU = gridU;
-            if (tilesU < gU) gU = (int)tilesU;
-            if (first) gridU = gU;
-            if ((rc = dispatch_bwd(sol->activation, n, m, bu, gU, s))) return rc;
+            if ((rc = plan_backward_launch(sol->activation, n, m, bU, bu, first, s))) return rc;
         }
         first = false;
     }
     if (backward) {
-        if ((rc = reduce_partials(gpU, gridU, lu, tu, beta, 1.f, s))) return rc;
-        if ((rc = reduce_partials(gpN, gridN, ln, tn, beta, 1.f, s))) return rc;
+        if ((rc = reduce_partials(bU.gpart, bU.grid, lu, tu, beta, 1.f, s))) return rc;
+        if ((rc = reduce_partials(bN.gpart, bN.grid, ln, tn, beta, 1.f, s))) return rc;
     }
     return PDEREAD_OK;
 }
@@ -759,6 +1105,7 @@ size_t pderead_extraction_gram_workspace_bytes(const pderead_net* sol, const pde
     if (to_netdev(sol, &U) != PDEREAD_OK || to_netdev(pde, &N) != PDEREAD_OK || M < 0) return 0;
     const long long chunk = round_up_ll(M < 8 * CHUNK_TARGET ? (M > 0 ? M : 1) : 8 * CHUNK_TARGET, CHUNK_ALIGN);
     size_t bytes = align_up(packed_floats(U) * 4, 256) + align_up(packed_floats(N) * 4, 256);
+    bytes += align_up(tc_image_bytes_bound(U), 256) + align_up(tc_image_bytes_bound(N), 256);
     bytes += align_up((size_t)chunk * (n + 1) * 4, 256) + align_up((size_t)chunk * 4, 256);
     return bytes + 8192;
 }
@@ -775,13 +1122,13 @@ int pderead_extraction_gram(const pderead_net* sol, const pderead_net* pde, int 
     if (M <= 0 || !d_coords || !ws || !d_G || !d_Atb || !d_btb) return PDEREAD_ERR_BAD_ARGUMENT;
     if (pderead_library_num_columns(n, K) < 1) return PDEREAD_ERR_BAD_ARGUMENT;
     const int J = jet_len(n, 0);
-    if ((rc = check_smem(U.W, U.L, U.din, J, false))) return rc;
-    if ((rc = check_smem(N.W, N.L, N.din, 1, false))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     Carver cv(ws, ws_bytes);
-    float* wtU = cv.take<float>(packed_floats(U));
-    float* wtN = cv.take<float>(packed_floats(N));
-    if (!cv.ok) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
+    FwdPlan plU, plN;
+    if ((rc = plan_forward(U, J, true, cv, &plU))) return rc;
+    if ((rc = plan_forward(N, 1, true, cv, &plN))) return rc;
+    if (!plU.tc && (rc = check_smem(U.W, U.L, U.din, J, false))) return rc;
+    if (!plN.tc && (rc = check_smem(N.W, N.L, N.din, 1, false))) return rc;
     const size_t per_point = (size_t)(n + 2) * 4;
     const size_t remain = ws_bytes - cv.used;
     long long chunk = (long long)((remain > 4096 ? remain - 4096 : 0) / per_point);
@@ -791,28 +1138,24 @@ int pderead_extraction_gram(const pderead_net* sol, const pderead_net* pde, int 
     float* dxn = cv.take<float>((size_t)chunk * (n + 1));
     float* bb = cv.take<float>((size_t)chunk);
     if (!cv.ok) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
-    if ((rc = pack(U, wtU, nullptr, s))) return rc;
-    if ((rc = pack(N, wtN, nullptr, s))) return rc;
+    if ((rc = plan_pack(U, plU, s))) return rc;
+    if ((rc = plan_pack(N, plN, s))) return rc;
     for (int64_t lo = 0; lo < M; lo += chunk) {
         const int64_t mc = (M - lo < chunk) ? (M - lo) : chunk;
         FwdArgs fu;
         memset(&fu, 0, sizeof(fu));
         fu.net = U;
-        fu.wt_packed = wtU;
         fu.in = d_coords + lo * 2;
         fu.M = mc;
-        fu.num_tiles = (mc + tile_points(J) - 1) / tile_points(J);
         fu.out0 = dxn;
-        if ((rc = dispatch_fwd(sol->activation, n, 0, fu, s))) return rc;
+        if ((rc = plan_launch(sol->activation, n, 0, plU, fu, s))) return rc;
         FwdArgs fn;
         memset(&fn, 0, sizeof(fn));
         fn.net = N;
-        fn.wt_packed = wtN;
         fn.in = dxn;
         fn.M = mc;
-        fn.num_tiles = (mc + tile_points(1) - 1) / tile_points(1);
         fn.out0 = bb;
-        if ((rc = dispatch_fwd(pde->activation, 0, 0, fn, s))) return rc;
+        if ((rc = plan_launch(pde->activation, 0, 0, plN, fn, s))) return rc;
         if ((rc = library_gram_launch(dxn, bb, mc, n, K, d_G, d_Atb, d_btb, s))) return rc;
     }
     return PDEREAD_OK;

@@ -75,6 +75,81 @@ struct BwdArgs {
     int accumulate;           // 0: this launch zeroes its partial-gradient vectors first
 };
 
+// ---- tensor-core path (tc_jet_kernels.cuh) ----------------------------------------------------
+struct TcGeom {
+    int mrows;        // MMA M: 64 (width <= 64, two point sets in the lane halves) or 128
+    int Kpad;         // width rounded up to 8
+    int NB;           // neurons per TMEM lane block (16 lanes for M = 64, 32 for M = 128)
+    int PC;           // points per chunk (per sub)
+    int NCpad;        // MMA N = accumulator columns per chunk (PC * J rounded up)
+    int TP;           // points per tile = subs * 2 chunks * PC
+    int a_bytes;      // bytes of one weight image half (hi or lo)
+    int a_rs;         // byte stride between 8-row groups of a weight image
+    int slot_bytes;   // bytes of one operand slot half (hi or lo)
+    int b_rs;         // byte stride between 8-column groups of an operand slot
+    int sub_stride;   // byte stride between the slot sets of the two subs
+    int nwbuf;        // weight buffers (1 or 2)
+    int tmem_cols;    // TMEM columns allocated (power of two)
+    size_t smem_bytes;
+};
+
+struct TcFwdArgs {
+    NetDev net;
+    TcGeom geom;
+    const float* wimg;        // [L][hi|lo] weight images (tc_pack_weights_kernel)
+    const float* in;          // [M][din]
+    long long M;
+    long long num_tiles;
+    float* out0;
+    float* out1;
+    float* stash;             // [L-1][M][J][mrows] pre-activations of hidden layers 1..L-1 (null unless STASH)
+    const float* dtm_in;
+    float* resid_out;
+    float* seed_out;
+    const float* grad_resid;
+    float seed_scale;
+    double* sumsq;
+};
+
+// geometry of the tensor-core reverse kernel (tc_jet_bwd_kernel)
+struct TcBwdGeom {
+    int mrows, Kpad, NB;
+    int Jp;           // columns per point (J rounded up so that operand stores stay 16-byte aligned)
+    int PC;           // points per chunk (per sub)
+    int nchunk;       // chunks per tile (2 = ping-pong, 1 when shared memory is short)
+    int NC;           // PC * Jp  (K of the weight-gradient products, multiple of 8)
+    int NCpad;        // N of the hbar products (NC rounded up to the MMA granularity)
+    int TP;           // points per tile
+    int a_bytes, a_rs;        // W^T image half
+    int zt_bytes, zt_rs;      // zbar as B operand of hbar = W^T zbar:   [n][k]  (k-contiguous, 144-byte k-group stride)
+    int za_bytes, za_rs;      // zbar as A operand of gW = zbar y^T:     [row][n] (n-contiguous)
+    int yb_bytes;             // y of the layer below as B operand of gW: [k][n]  (same row stride za_rs)
+    int npad_w;               // N of the weight-gradient products (Kpad rounded up to the MMA granularity)
+    int set_bytes;            // one (sub, chunk) set: hi|lo of zt, za, yb
+    int sub_stride;
+    int nwbuf;
+    int gcol0;                // first TMEM column of the weight-gradient accumulators
+    int tmem_cols;
+    size_t smem_bytes;
+};
+
+struct TcBwdArgs {
+    NetDev net;
+    GradLayout lay;
+    TcBwdGeom geom;
+    const float* wimg;        // transposed weight images: index lv-1 for hidden layer lv = 1..L-1, index L-1 = input layer (for gin)
+    const float* in;          // [M][din]
+    long long M;
+    long long num_tiles;
+    const float* stash;       // [L-1][M][J][mrows]
+    const float* g0;
+    const float* g1;
+    float g0_scale, g1_scale;
+    float* gin;               // [M][din] or null (J == 1 only)
+    float* gpart;             // [gridDim.x][lay.total]
+    int accumulate;
+};
+
 struct Segment {
     float* dst;
     int off;
@@ -92,6 +167,11 @@ template <int ACT, int NX, int NT>
 int bwd_grid(int W, int L, int din, long long num_tiles, int* grid_out);
 template <int ACT, int NX, int NT>
 int launch_bwd_impl(const BwdArgs& a, int grid, cudaStream_t stream);
+
+template <int ACT, int NX, int NT>
+int launch_tc_fwd(const TcFwdArgs& a, cudaStream_t stream);
+template <int ACT, int NX, int NT>
+int launch_tc_bwd(const TcBwdArgs& a, int grid, cudaStream_t stream);
 
 // geometry helpers shared by host code
 inline int jet_len(int nx, int nt) { return 1 + nx + nt; }

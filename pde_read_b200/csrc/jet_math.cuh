@@ -39,7 +39,26 @@ PDR_HD constexpr int jet_index(int S, int k) { return k == 0 ? 0 : (S == 0 ? k :
 // ---------------------------------------------------------------------------------------------
 // scalar helpers (overloaded so the float path uses the single-precision CUDA math functions)
 // ---------------------------------------------------------------------------------------------
-PDR_HD float  pdr_tanh(float v)  { return tanhf(v); }
+// float tanh: branch-free, two MUFU ops.  |x| < 0.25: odd Taylor polynomial through x^11 (truncation
+// < 1e-10); otherwise 1 - 2/(exp(2|x|) + 1) with ex2.approx / rcp.approx (absolute error ~1.5e-7).
+PDR_HD float pdr_tanh(float v) {
+#if defined(__CUDA_ARCH__)
+    const float ax = fabsf(v);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    const float big = copysignf(fmaf(-2.f, r, 1.f), v);
+    const float x2 = v * v;
+    float p = fmaf(x2, -0.0088632355f, 0.021869489f);
+    p = fmaf(x2, p, -0.053968254f);
+    p = fmaf(x2, p, 0.13333333f);
+    p = fmaf(x2, p, -0.33333333f);
+    const float small = fmaf(v * x2, p, v);
+    return ax < 0.25f ? small : big;
+#else
+    return tanhf(v);
+#endif
+}
 PDR_HD double pdr_tanh(double v) { return tanh(v); }
 PDR_HD void pdr_sincos(float v, float* s, float* c)    { *s = sinf(v); *c = cosf(v); }
 PDR_HD void pdr_sincos(double v, double* s, double* c) { *s = sin(v); *c = cos(v); }

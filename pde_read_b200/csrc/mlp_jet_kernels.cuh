@@ -312,7 +312,7 @@ __device__ __forceinline__ void wgrad_tiles(const float* __restrict__ ZB, const 
 #pragma unroll
                 for (int tk = 0; tk < TK; ++tk) {
                     const int k = mk + MK * tk;
-                    if (k < W) gw[(size_t)i * W + k] += acc[ti][tk];
+                    if (k < W) atomicAdd(&gw[(size_t)i * W + k], acc[ti][tk]);   // private to this CTA; RED avoids the load round trip
                 }
             }
         }
