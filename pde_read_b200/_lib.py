@@ -18,7 +18,7 @@ MAX_LIBRARY_COLUMNS = 256
 ACT_CODES = {"Tanh": 0, "Sin": 1, "Rational": 2}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpderead_b200.so")
+LIB_PATH = os.environ.get("PDEREAD_LIB") or os.path.join(_HERE, "libpderead_b200.so")
 
 
 class PdereadError(RuntimeError):

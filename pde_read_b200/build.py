@@ -15,13 +15,17 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJDIR = os.path.join(CSRC, "_build")
-LIB = os.path.join(HERE, "libpderead_b200.so")
+# tuning experiments: PDR_VARIANT=<tag> PDR_EXTRA_CFLAGS="-DX=1 .." builds libpderead_b200_<tag>.so beside the
+# product library (load it with PDEREAD_LIB=<path>); the product build uses neither variable.
+VARIANT = os.environ.get("PDR_VARIANT", "")
+OBJDIR = os.path.join(CSRC, "_build" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libpderead_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC = os.environ.get("NVCC", "nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE]
+CFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE] + \
+    os.environ.get("PDR_EXTRA_CFLAGS", "").split()
 
 # (NX, NT) combinations the kernels are instantiated for; backward only where it is needed:
 # plain MLP (0,0) and every combination with a time series (Evaluate_Derivatives always has m >= 1).

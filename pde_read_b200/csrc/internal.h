@@ -16,9 +16,25 @@ constexpr int TNP = 12;         // chunk length in the packed weights (keeps row
 constexpr int MAX_WARPS = 12;   // warps per CTA (chunks beyond that are looped over)
 
 // points per lane as a function of the jet length J = 1 + NX + NT
+#ifndef PDR_PPL_J1
+#define PDR_PPL_J1 2
+#endif
+#ifndef PDR_PPL_J4
+#define PDR_PPL_J4 1
+#endif
 template <int J>
 struct PointsPerLane {
-    static constexpr int v = (J == 1) ? 4 : ((J <= 4) ? 2 : 1);
+    static constexpr int v = (J == 1) ? PDR_PPL_J1 : ((J <= 4) ? PDR_PPL_J4 : 1);
+};
+
+// Register budget of the CUDA-core kernels.  They are latency-bound in the activation-jet code, so resident
+// warps matter more than registers per thread: the launch bound is only a handle on ptxas' register cap,
+// 65536 / max_threads (blocks are at most MAX_WARPS * 32 threads).  J <= 4: 96 registers -> 4 CTAs of 5 warps
+// per SM at width 50 (tile = 32 points, 53 KB of shared memory); J = 5: 128; J >= 6: 168 (shared memory
+// allows 2 CTAs at most there).  Measured on C2: 2 -> 4 CTAs/SM = 1.29x on the whole step.
+template <int J>
+struct RegCap {
+    static constexpr int max_threads = (J <= 4) ? 640 : (J == 5 ? 512 : 384);
 };
 
 struct NetDev {
@@ -175,7 +191,7 @@ int launch_tc_bwd(const TcBwdArgs& a, int grid, cudaStream_t stream);
 
 // geometry helpers shared by host code
 inline int jet_len(int nx, int nt) { return 1 + nx + nt; }
-inline int points_per_lane(int J) { return (J == 1) ? 4 : ((J <= 4) ? 2 : 1); }
+inline int points_per_lane(int J) { return (J == 1) ? PDR_PPL_J1 : ((J <= 4) ? PDR_PPL_J4 : 1); }
 inline int tile_points(int J) { return 32 * points_per_lane(J); }
 inline int h_stride(int J) { return J * tile_points(J) + 4; }
 size_t fwd_smem_bytes(int W, int din, int J, int nwarps);

@@ -22,6 +22,7 @@
 #include "internal.h"
 #include "jet_math.cuh"
 
+
 namespace pdr {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -64,7 +65,7 @@ __device__ __forceinline__ void input_layer_jet(const NetDev& net, const float* 
 // forward
 // =============================================================================================
 template <int ACT, int NX, int NT, bool STASH>
-__global__ void __launch_bounds__(MAX_WARPS * 32) mlp_jet_fwd_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_kernel(const FwdArgs a) {
     constexpr int J = 1 + NX + NT;
     constexpr int PPL = PointsPerLane<J>::v;
     constexpr int TP = 32 * PPL;
@@ -320,7 +321,7 @@ __device__ __forceinline__ void wgrad_tiles(const float* __restrict__ ZB, const 
 }
 
 template <int ACT, int NX, int NT>
-__global__ void __launch_bounds__(MAX_WARPS * 32) mlp_jet_bwd_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_kernel(const BwdArgs a) {
     constexpr int J = 1 + NX + NT;
     constexpr int PPL = PointsPerLane<J>::v;
     constexpr int TP = 32 * PPL;
