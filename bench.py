@@ -175,6 +175,14 @@ def time_cpu_reference(c, sd_u, sd_n, sample_points, steps, warmup, budget_s=150
                 ms_per_step=1e3 * total / steps)
 
 
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -262,7 +270,7 @@ def main():
             return loss
 
     # stage events: one per kernel launch of the library, for every timed step
-    MAXEV = 64
+    MAXEV = 160
     def new_events(n):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
         for e in evs:
@@ -352,34 +360,61 @@ def main():
     peak_ffma = F.fma_peak_probe(dev, 0, 8192)
     peak_ffma2 = F.fma_peak_probe(dev, 1, 8192)
     peak = max(peak_ffma, peak_ffma2)
+    peak_src = ("pderead_fma_peak_probe measured in this run (FFMA %.1f, FFMA2 %.1f TFLOP/s); MEASURED_PEAKS.json "
+                "carries HBM and bf16-tensor peaks only, and this path is bound by FP32 FMA issue" % (peak_ffma, peak_ffma2))
     stage_ms = per_stage.mean(axis=0) if nrec else np.zeros(0)
+    traffic_tab = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as fh:
+            traffic_tab = json.load(fh)
+    except Exception:
+        pass
     roof = None
-    if not c.get("extraction") and nrec >= 8:
-        # launches of one fused step with a single chunk:
-        # 0 pack(U) 1 pack(N) 2 U-jets fwd 3 N fwd+residual 4 N bwd 5 U-jets bwd 6 reduce(U) 7 reduce(N)
-        names = ["pack_U", "pack_N", "mlp_jet_fwd<U>", "mlp_jet_fwd<N>", "mlp_jet_bwd<N>", "mlp_jet_bwd<U>",
-                 "reduce_partials<U>", "reduce_partials<N>"]
-        if nrec == 8:
-            k_dom = 5
-            flops_launch = 2.0 * FU * M_local                   # reverse pass of U = 2x its forward
-            dur_ms = float(stage_ms[k_dom])
-            ach = flops_launch / (dur_ms * 1e-3) / 1e12
-            roof = {"bound": "fp32_fma", "kernel": "mlp_jet_bwd_kernel (U network)", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak,
-                    "peak_source": "pderead_fma_peak_probe measured in this run (FFMA %.1f, FFMA2 %.1f TFLOP/s); "
-                                   "MEASURED_PEAKS.json has no FP32-FMA entry" % (peak_ffma, peak_ffma2),
-                    "traffic": None, "kernel_ms": dur_ms, "algorithmic_flops_per_launch": flops_launch,
-                    "stage_ms": {n_: float(v) for n_, v in zip(names, stage_ms)},
-                    "whole_step": {"achieved": 3.0 * (FU + FN) * M_local / (ms_per_step * 1e-3) / 1e12,
-                                   "frac": 3.0 * (FU + FN) * M_local / (ms_per_step * 1e-3) / 1e12 / peak},
-                    "hbm": {"algorithmic_bytes_per_point": 12,
-                            "achieved_gbs": 12.0 * M_local / (ms_per_step * 1e-3) / 1e9}}
+    if not c.get("extraction") and nrec >= 8 and (nrec - 4) % 4 == 0:
+        # launches of one fused step: pack(U) pack(N) | per chunk of <= 131072 points: U-jets fwd, N fwd + residual,
+        # N reverse, U reverse | reduce(U) reduce(N).  The U reverse kernel dominates; its launches are summed.
+        nchunk = (nrec - 4) // 4
+        per_chunk = stage_ms[2:2 + 4 * nchunk].reshape(nchunk, 4).sum(axis=0)
+        names = ["mlp_jet_fwd<U>", "mlp_jet_fwd<N>", "mlp_jet_bwd<N>", "mlp_jet_bwd<U>"]
+        dur_ms = float(per_chunk[3])
+        flops = 2.0 * FU * M_local                           # reverse pass of U = 2x its forward
+        ach = flops / (dur_ms * 1e-3) / 1e12
+        tkey = "%s:mlp_jet_bwd<U>" % args.config
+        traffic = traffic_tab.get(tkey)
+        roof = {"bound": "fp32_fma", "kernel": "mlp_jet_bwd_kernel (U network), %d launch(es) per step" % nchunk,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src,
+                "traffic": traffic, "kernel_ms": dur_ms / nchunk, "algorithmic_flops_per_launch": flops / nchunk,
+                "stage_ms": dict({"pack_U": float(stage_ms[0]), "pack_N": float(stage_ms[1])},
+                                 **{n_: float(v) for n_, v in zip(names, per_chunk)},
+                                 **{"reduce_partials<U>": float(stage_ms[-2]), "reduce_partials<N>": float(stage_ms[-1])}),
+                "whole_step": {"achieved": 3.0 * (FU + FN) * M_local / (ms_per_step * 1e-3) / 1e12,
+                               "frac": 3.0 * (FU + FN) * M_local / (ms_per_step * 1e-3) / 1e12 / peak},
+                "hbm": {"algorithmic_bytes_per_point": 12, "achieved_gbs": 12.0 * M_local / (ms_per_step * 1e-3) / 1e9,
+                        "peak_gbs": measured_peaks().get("hbm_gbs")}}
+    elif c.get("extraction") and nrec >= 6 and (nrec - 3) % 3 == 0:
+        # pack(U) pack(N) | per chunk: U-jets fwd (no t-series), N fwd, fused library + Gram | RFE + ranking
+        nchunk = (nrec - 3) // 3
+        per_chunk = stage_ms[2:2 + 3 * nchunk].reshape(nchunk, 3).sum(axis=0)
+        Jx = 1 + c["n"]
+        FUx = 2 * (2 * c["WU"] + (c["LU"] - 1) * c["WU"] ** 2 * Jx + c["WU"] * Jx)
+        dur_ms = float(per_chunk[0])
+        flops = float(FUx) * M_local
+        ach = flops / (dur_ms * 1e-3) / 1e12
+        roof = {"bound": "fp32_fma", "kernel": "mlp_jet_fwd_kernel (U network, x-series only), %d launch(es) per step" % nchunk,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src,
+                "traffic": traffic_tab.get("%s:mlp_jet_fwd<U>" % args.config), "kernel_ms": dur_ms / nchunk,
+                "algorithmic_flops_per_launch": flops / nchunk,
+                "stage_ms": {"pack_U": float(stage_ms[0]), "pack_N": float(stage_ms[1]), "mlp_jet_fwd<U>": float(per_chunk[0]),
+                             "fwd<N>": float(per_chunk[1]), "library_gram": float(per_chunk[2]), "rfe": float(stage_ms[-1])},
+                "whole_step": {"achieved": float(FUx + FN) * M_local / (ms_per_step * 1e-3) / 1e12,
+                               "frac": float(FUx + FN) * M_local / (ms_per_step * 1e-3) / 1e12 / peak},
+                "hbm": {"algorithmic_bytes_per_point": 8, "achieved_gbs": 8.0 * M_local / (ms_per_step * 1e-3) / 1e9,
+                        "peak_gbs": measured_peaks().get("hbm_gbs")}}
     if roof is None:
         flops_step = (3.0 * (FU + FN) if not c.get("extraction") else float(FU + FN)) * M_local
         ach = flops_step / (ms_per_step * 1e-3) / 1e12
         roof = {"bound": "fp32_fma", "kernel": "whole step (stage events: %d)" % nrec, "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                "peak_source": "pderead_fma_peak_probe measured in this run",
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                 "stage_ms": [float(v) for v in stage_ms]}
 
     # ------------------------------------------------ CPU baseline beside it (bounded sample)
@@ -397,7 +432,9 @@ def main():
         "config": {"workload": args.config + ": " + c["desc"], "points_per_step_total": M_total,
                    "points_per_gpu": M_local, "weights": "random init (reference initialiser), seed 1234",
                    "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-                   "parallelism": "points sharded over %d GPU(s), weights replicated" % world},
+                   "parallelism": "points sharded over %d GPU(s), weights replicated" % world,
+                   "tensor_cores": os.environ.get("PDEREAD_TC", "auto") +
+                                   " (auto: tcgen05 kernels for forward-only calls of width > 64 and depth >= 3; CUDA cores on the gradient path)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(M_local * 2 * 4),
                 "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},

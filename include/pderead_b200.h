@@ -182,7 +182,7 @@ int pderead_debug_stage_events(void* const* events, int count);
 int pderead_debug_stage_events_recorded(void);
 /* Tensor-core policy for the hidden-layer products (tcgen05, 3xTF32; widths 8..128, depth >= 2):
  *   0 off   - CUDA-core kernels everywhere;
- *   1 auto  - default: forward-only calls of networks wider than 64 use the tensor cores, the gradient
+ *   1 auto  - default: forward-only calls of networks wider than 64 (>= 3 hidden layers) use the tensor cores, the gradient
  *             path stays on the CUDA cores (fp32-exact accumulation);
  *   2 force - tensor cores wherever the shape is supported, including the reverse pass.
  * Also selectable with the environment variable PDEREAD_TC=off|auto|force.  Returns the previous mode. */

@@ -267,7 +267,7 @@ static bool order_supported(int nx, int nt) {
 // tensor-core path: geometry, weight images, dispatch
 // ---------------------------------------------------------------------------------------------
 // Tensor-core policy.  0 = off: CUDA-core kernels everywhere.  1 = auto (default): forward-only calls of
-// networks wider than 64 run on the tensor cores (measured 1.6-2x faster there, and inside the stated
+// networks wider than 64 with at least 3 hidden layers run on the tensor cores (measured 1.6-2x faster there, and inside the stated
 // derivative / residual tolerances); everything on the gradient path stays on the CUDA cores, because the
 // tensor core truncates inside its accumulation and 3xTF32 lands at ~1e-6 relative error per network
 // instead of fp32's ~1e-7, which the residual cancellation of a trained network amplifies in the
@@ -286,7 +286,7 @@ static bool tc_allowed(const NetDev& n, bool gradient_path) {
     const int m = tc_mode();
     if (m == 0) return false;
     if (m == 2) return true;
-    return !gradient_path && n.W > 64;
+    return !gradient_path && n.W > 64 && n.L >= 3;   // (2 x 100 plain nets measured slower: the output product is half the work)
 }
 
 static int round_up_i(int v, int a) { return (v + a - 1) / a * a; }

@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_jet_fwd_kernel(const TcFwdAr
     if (warp == TC_EPI_WARPS + 1) {
         // ===== weight loader: one bulk copy (hi|lo image of one layer) per product =====
         if (lane == 0) {
-            for (long long s = 0; s < total_gemms; ++s) {
+            // L <= nwbuf: every product keeps its own buffer, the images are loaded once and stay resident
+            const long long nload = (L <= g.nwbuf) ? (total_gemms < L ? total_gemms : L) : total_gemms;
+            for (long long s = 0; s < nload; ++s) {
                 const int b = (int)(s % g.nwbuf);
                 if (s >= g.nwbuf) mbar_wait(&wfree[b], (uint32_t)(((s / g.nwbuf) - 1) & 1));
                 const int gi = (int)(s % L);        // product index inside the tile: 0..L-2 hidden, L-1 output
@@ -138,9 +140,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_jet_fwd_kernel(const TcFwdAr
             const uint32_t corr_off = 2u * (uint32_t)g.NCpad;
             const int ksteps = g.Kpad >> 3;
             uint32_t full_ph[2] = {0, 0};
+            const bool resident = (L <= g.nwbuf);
             for (long long s = 0; s < total_gemms; ++s) {
-                const int b = (int)(s % g.nwbuf);
-                mbar_wait(&wfull[b], (uint32_t)((s / g.nwbuf) & 1));
+                const int b = resident ? (int)(s % L) : (int)(s % g.nwbuf);
+                if (!resident || s < L) mbar_wait(&wfull[b], (uint32_t)((s / g.nwbuf) & 1));
                 const uint32_t a_hi = smem_u32(wbuf + (size_t)b * img_bytes), a_lo = a_hi + (uint32_t)g.a_bytes;
                 for (int c = 0; c < 2; ++c) {
                     mbar_wait(&full[c], full_ph[c]);
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_jet_fwd_kernel(const TcFwdAr
                     }
                     mma_commit(&dready[c]);
                 }
-                mma_commit(&wfree[b]);
+                if (!resident) mma_commit(&wfree[b]);
             }
         }
     } else {
@@ -409,7 +412,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_jet_bwd_kernel(const TcBwdAr
     if (warp == TC_EPI_WARPS + 1) {
         // ===== weight loader =====
         if (lane == 0) {
-            for (long long s = 0; s < total_prod; ++s) {
+            const long long nload = (nprod <= g.nwbuf) ? (total_prod < nprod ? total_prod : nprod) : total_prod;
+            for (long long s = 0; s < nload; ++s) {
                 const int b = (int)(s % g.nwbuf);
                 if (s >= g.nwbuf) mbar_wait(&wfree[b], (uint32_t)(((s / g.nwbuf) - 1) & 1));
                 const int idx = (int)(s % nprod);
@@ -428,10 +432,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_jet_bwd_kernel(const TcBwdAr
             const uint32_t corr_off = (uint32_t)(NCH * g.NCpad);   // correction-term accumulators of the hbar products
             uint32_t full_ph[2] = {0, 0};
             for (long long s = 0; s < total_prod; ++s) {
-                const int b = (int)(s % g.nwbuf);
                 const int idx = (int)(s % nprod);
+                const int b = (nprod <= g.nwbuf) ? idx : (int)(s % g.nwbuf);
                 const bool first_tile = ((s / nprod) % TC_FLUSH_TILES) == 0;   // accumulators were flushed: restart them
-                mbar_wait(&wfull[b], (uint32_t)((s / g.nwbuf) & 1));
+                const bool resident = (nprod <= g.nwbuf);
+                if (!resident || s < nprod) mbar_wait(&wfull[b], (uint32_t)((s / g.nwbuf) & 1));
                 const uint32_t a_hi = smem_u32(wbuf + (size_t)b * img_bytes), a_lo = a_hi + (uint32_t)g.a_bytes;
                 for (int c = 0; c < NCH; ++c) {
                     mbar_wait(&full[c], full_ph[c]);
@@ -474,7 +479,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_jet_bwd_kernel(const TcBwdAr
                     }
                     mma_commit(&dready[c]);
                 }
-                mma_commit(&wfree[b]);
+                if (!resident) mma_commit(&wfree[b]);
             }
         }
     } else {
