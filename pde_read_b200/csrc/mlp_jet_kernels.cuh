@@ -44,6 +44,29 @@ __device__ __forceinline__ void load_ab(const NetDev& net, int l, float* ab) {
     }
 }
 
+
+// One k-step of a layer product, acc[q][j][n] += h[q][j] * w[n] for the TN weights of this warp's chunk,
+// issued as packed fma.rn.f32x2 (two FMAs per instruction, same rounding as fmaf): the weights arrive as
+// aligned pairs from the 16-byte loads, the activation is duplicated into a pair.
+template <int PPL, int J>
+__device__ __forceinline__ void product_step(float2 (&acc)[PPL][J][TN / 2], const float* __restrict__ hk, int TP,
+                                             const float* __restrict__ wk) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(wk));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(wk) + 1);
+    const float4 b2 = __ldg(reinterpret_cast<const float4*>(wk) + 2);
+    const float2 bw[TNP / 2] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                make_float2(b1.z, b1.w), make_float2(b2.x, b2.y), make_float2(b2.z, b2.w)};
+#pragma unroll
+    for (int q = 0; q < PPL; ++q)
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const float av = hk[j * TP + q * 32];
+            const float2 a2 = make_float2(av, av);
+#pragma unroll
+            for (int n = 0; n < TN / 2; ++n) acc[q][j][n] = __ffma2_rn(a2, bw[n], acc[q][j][n]);
+        }
+}
+
 // pre-activation jet of hidden layer 0 (the input layer) for neuron i at tile point pt:
 // z_0 = b + sum_d W[i][d] in[d];  the x-series is seeded by input column 1 and the t-series by
 // input column 0 (coords are (t, x), reference PDE_Residual.py:33-34).
@@ -136,37 +159,36 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
             const bool last = (l == L - 1);
             load_ab<ACT>(net, l, ab);
             for (int c = warp; c < NC; c += nwarps) {
-                float acc[PPL][J][TN];
+                float2 acc2[PPL][J][TN / 2];
 #pragma unroll
-                for (int n = 0; n < TN; ++n) {
+                for (int n = 0; n < TN; n += 2) {
                     const int i = c * TN + n;
-                    const float bv = (i < W) ? __ldg(bias + i) : 0.f;
+                    const float bv0 = (i < W) ? __ldg(bias + i) : 0.f, bv1 = (i + 1 < W) ? __ldg(bias + i + 1) : 0.f;
 #pragma unroll
                     for (int q = 0; q < PPL; ++q) {
-                        acc[q][0][n] = bv;
+                        acc2[q][0][n / 2] = make_float2(bv0, bv1);
 #pragma unroll
-                        for (int j = 1; j < J; ++j) acc[q][j][n] = 0.f;
+                        for (int j = 1; j < J; ++j) acc2[q][j][n / 2] = make_float2(0.f, 0.f);
                     }
                 }
                 const float* wk = wp + c * TNP;
                 const float* hk = Hin + lane;
 #pragma unroll 2
                 for (int k = 0; k < W; ++k) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(wk));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(wk) + 1);
-                    const float4 b2 = __ldg(reinterpret_cast<const float4*>(wk) + 2);
-                    const float bw[TNP] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
-#pragma unroll
-                    for (int q = 0; q < PPL; ++q)
-#pragma unroll
-                        for (int j = 0; j < J; ++j) {
-                            const float av = hk[j * TP + q * 32];
-#pragma unroll
-                            for (int n = 0; n < TN; ++n) acc[q][j][n] = fmaf(av, bw[n], acc[q][j][n]);
-                        }
+                    product_step<PPL, J>(acc2, hk, TP, wk);
                     wk += NC * TNP;
                     hk += HS;
                 }
+                float acc[PPL][J][TN];
+#pragma unroll
+                for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                    for (int j = 0; j < J; ++j)
+#pragma unroll
+                        for (int n = 0; n < TN / 2; ++n) {
+                            acc[q][j][2 * n] = acc2[q][j][n].x;
+                            acc[q][j][2 * n + 1] = acc2[q][j][n].y;
+                        }
 #pragma unroll
                 for (int n = 0; n < TN; ++n) {
                     const int i = c * TN + n;
@@ -281,11 +303,13 @@ __device__ __forceinline__ void wgrad_tiles(const float* __restrict__ ZB, const 
             const int k = mk + MK * tk;
             bp[tk] = reinterpret_cast<const float4*>(HP + (size_t)(k < W ? k : mk) * HS);
         }
-        float acc[TI][TK];
+        // packed fma.rn.f32x2: each output keeps two partial sums (even / odd reduction index), the operand
+        // pairs are the .xy / .zw halves of the 16-byte loads
+        float2 acc2[TI][TK];
 #pragma unroll
         for (int ti = 0; ti < TI; ++ti)
 #pragma unroll
-            for (int tk = 0; tk < TK; ++tk) acc[ti][tk] = 0.f;
+            for (int tk = 0; tk < TK; ++tk) acc2[ti][tk] = make_float2(0.f, 0.f);
         const int R4 = R >> 2;
 #pragma unroll 2
         for (int r = 0; r < R4; ++r) {
@@ -298,14 +322,17 @@ __device__ __forceinline__ void wgrad_tiles(const float* __restrict__ ZB, const 
             for (int ti = 0; ti < TI; ++ti)
 #pragma unroll
                 for (int tk = 0; tk < TK; ++tk) {
-                    float s = acc[ti][tk];
-                    s = fmaf(av[ti].x, bv[tk].x, s);
-                    s = fmaf(av[ti].y, bv[tk].y, s);
-                    s = fmaf(av[ti].z, bv[tk].z, s);
-                    s = fmaf(av[ti].w, bv[tk].w, s);
-                    acc[ti][tk] = s;
+                    float2 s2 = acc2[ti][tk];
+                    s2 = __ffma2_rn(make_float2(av[ti].x, av[ti].y), make_float2(bv[tk].x, bv[tk].y), s2);
+                    s2 = __ffma2_rn(make_float2(av[ti].z, av[ti].w), make_float2(bv[tk].z, bv[tk].w), s2);
+                    acc2[ti][tk] = s2;
                 }
         }
+        float acc[TI][TK];
+#pragma unroll
+        for (int ti = 0; ti < TI; ++ti)
+#pragma unroll
+            for (int tk = 0; tk < TK; ++tk) acc[ti][tk] = acc2[ti][tk].x + acc2[ti][tk].y;
 #pragma unroll
         for (int ti = 0; ti < TI; ++ti) {
             const int i = mi + MI * ti;
@@ -434,32 +461,31 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                 // (c) HP = hbar^{lv}[k] = sum_i W_l[i][k] ZB[i]
                 const float* wp = a.wn_packed + (size_t)(l - 1) * W * NC * TNP;
                 for (int c = warp; c < NC; c += nwarps) {
+                    float2 acc2[PPL][J][TN / 2];
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                        for (int j = 0; j < J; ++j)
+#pragma unroll
+                            for (int n = 0; n < TN / 2; ++n) acc2[q][j][n] = make_float2(0.f, 0.f);
+                    const float* wi = wp + c * TNP;
+                    const float* zi = ZB + lane;
+#pragma unroll 2
+                    for (int i = 0; i < W; ++i) {
+                        product_step<PPL, J>(acc2, zi, TP, wi);
+                        wi += NC * TNP;
+                        zi += HS;
+                    }
                     float acc[PPL][J][TN];
 #pragma unroll
                     for (int q = 0; q < PPL; ++q)
 #pragma unroll
                         for (int j = 0; j < J; ++j)
 #pragma unroll
-                            for (int n = 0; n < TN; ++n) acc[q][j][n] = 0.f;
-                    const float* wi = wp + c * TNP;
-                    const float* zi = ZB + lane;
-#pragma unroll 2
-                    for (int i = 0; i < W; ++i) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(wi));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(wi) + 1);
-                        const float4 b2 = __ldg(reinterpret_cast<const float4*>(wi) + 2);
-                        const float bw[TNP] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
-#pragma unroll
-                        for (int q = 0; q < PPL; ++q)
-#pragma unroll
-                            for (int j = 0; j < J; ++j) {
-                                const float av = zi[j * TP + q * 32];
-#pragma unroll
-                                for (int n = 0; n < TN; ++n) acc[q][j][n] = fmaf(av, bw[n], acc[q][j][n]);
+                            for (int n = 0; n < TN / 2; ++n) {
+                                acc[q][j][2 * n] = acc2[q][j][n].x;
+                                acc[q][j][2 * n + 1] = acc2[q][j][n].y;
                             }
-                        wi += NC * TNP;
-                        zi += HS;
-                    }
 #pragma unroll
                     for (int n = 0; n < TN; ++n) {
                         const int k = c * TN + n;
