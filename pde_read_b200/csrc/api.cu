@@ -61,16 +61,35 @@ __global__ void pack_weights_kernel(NetDev net, float* wt, float* wn) {
     }
 }
 
-// dst = beta*dst + scale * sum_over_parts(gpart)
-__global__ void reduce_partials_kernel(const float* __restrict__ gpart, int nparts, int stride, SegmentTable tab,
-                                       float beta, float scale) {
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < stride; e += gridDim.x * blockDim.x) {
+// dst = beta*dst + scale * sum_over_parts(gpart).  Block = 32 consecutive elements x 8 slices of the partial
+// vectors; every thread sums its slice with four independent accumulators (the loads are the cost), the
+// slices are combined through shared memory in a fixed order, so the result is bit-reproducible.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ gpart, int nparts, int stride,
+                                                              SegmentTable tab, float beta, float scale) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + tx;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (e < stride) {
+        int p = ty;
+        for (; p + 24 < nparts; p += 32) {
+            a0 += gpart[(size_t)p * stride + e];
+            a1 += gpart[(size_t)(p + 8) * stride + e];
+            a2 += gpart[(size_t)(p + 16) * stride + e];
+            a3 += gpart[(size_t)(p + 24) * stride + e];
+        }
+        for (; p < nparts; p += 8) a0 += gpart[(size_t)p * stride + e];
+    }
+    red[ty][tx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ty == 0 && e < stride) {
         int s = -1;
         for (int t = 0; t < tab.n; ++t)
             if (e >= tab.seg[t].off && e < tab.seg[t].off + tab.seg[t].count) { s = t; break; }
-        if (s < 0) continue;
+        if (s < 0) return;
         float acc = 0.f;
-        for (int p = 0; p < nparts; ++p) acc += gpart[(size_t)p * stride + e];
+#pragma unroll
+        for (int y = 0; y < 8; ++y) acc += red[y][tx];
         float* d = tab.seg[s].dst + (e - tab.seg[s].off);
         *d = (beta == 0.f ? 0.f : beta * (*d)) + scale * acc;
     }
@@ -542,8 +561,8 @@ static int pack(const NetDev& n, float* wt, float* wn, cudaStream_t s) {
 
 static int reduce_partials(const float* gpart, int nparts, const GradLayout& lay, const SegmentTable& tab, float beta,
                            float scale, cudaStream_t s) {
-    const int blocks = (lay.total + 127) / 128;
-    reduce_partials_kernel<<<blocks, 128, 0, s>>>(gpart, nparts, lay.total, tab, beta, scale);
+    const int blocks = (lay.total + 31) / 32;
+    reduce_partials_kernel<<<blocks, 256, 0, s>>>(gpart, nparts, lay.total, tab, beta, scale);
     PDR_CUDA_CHECK(cudaGetLastError());
     stage_mark(s);
     return PDEREAD_OK;
