@@ -302,6 +302,67 @@ def collocation_loss_grad(sol_spec, sol_tensors, pde_spec, pde_tensors, m: int, 
 
 
 # ----------------------------------------------------------------------------------------------
+# CUDA-graph replay of the fused step (launch-bound when the point set is small, e.g. the reference's
+# default 5000 collocation points: ~10 launches of ~30 us of work each)
+# ----------------------------------------------------------------------------------------------
+import os as _os
+
+USE_CUDA_GRAPHS = _os.environ.get("PDEREAD_CUDA_GRAPHS", "0") not in ("0", "", "off")
+_GRAPH_CACHE = {}
+_GRAPH_CACHE_MAX = 8
+
+
+def collocation_loss_grad_graphed(sol_spec, sol_tensors, pde_spec, pde_tensors, m: int, n: int, coords: torch.Tensor,
+                                  M_total: Optional[int] = None, extra_tail: int = 0):
+    """Same result as collocation_loss_grad(...)[:4] + (None,), but the kernel sequence is captured once
+    into a CUDA graph per (networks, orders, point count) and replayed: one launch per step instead of ten.
+    The parameter tensors are read in place at replay time, so optimiser updates are seen; a graph is rebuilt
+    if any parameter tensor is replaced by a new one."""
+    coords = _check_tensor(coords.detach(), "Coords")
+    M = coords.shape[0]
+    if M_total is None:
+        M_total = M
+    dev = coords.device
+    key = (dev.index, sol_spec, pde_spec, m, n, M, int(M_total), extra_tail,
+           tuple(t.data_ptr() for t in sol_tensors), tuple(t.data_ptr() for t in pde_tensors))
+    ent = _GRAPH_CACHE.get(key)
+    if ent is None:
+        if len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
+            _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
+        static_coords = coords.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm-up: grows the workspace outside the capture
+            for _ in range(2):
+                collocation_loss_grad(sol_spec, sol_tensors, pde_spec, pde_tensors, m, n, static_coords,
+                                      M_total=M_total, extra_tail=extra_tail)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ss, flat, vu, vn, _ = collocation_loss_grad(sol_spec, sol_tensors, pde_spec, pde_tensors, m, n,
+                                                        static_coords, M_total=M_total, extra_tail=extra_tail)
+        ent = (graph, static_coords, ss, flat, [tuple(v.shape) for v in vu], [tuple(v.shape) for v in vn],
+               list(sol_tensors) + list(pde_tensors))      # keep the parameter tensors alive with the graph
+        _GRAPH_CACHE[key] = ent
+    graph, static_coords, ss, flat, shu, shn, _keep = ent
+    static_coords.copy_(coords)
+    graph.replay()
+    out_flat = flat.clone()                                  # the static buffers are overwritten by the next replay
+    views, off = [], 0
+    for shape in shu + shn:
+        numel = 1
+        for d in shape:
+            numel *= d
+        views.append(out_flat[off:off + numel].view(shape))
+        off += (numel + 3) // 4 * 4
+    return ss.clone(), out_flat, views[:len(shu)], views[len(shu):], None
+
+
+def release_graphs() -> None:
+    _GRAPH_CACHE.clear()
+
+
+# ----------------------------------------------------------------------------------------------
 # autograd functions
 # ----------------------------------------------------------------------------------------------
 class SolDerivativesFn(torch.autograd.Function):
@@ -374,8 +435,9 @@ class CollocationLossFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[7:])
         M_total = reducer.total_points(M) if reducer is not None else M
         if need_grad:
-            ss, flat, vu, vn, _ = collocation_loss_grad(sol_spec, sol_t, pde_spec, pde_t, m, n, coords,
-                                                        M_total=M_total, extra_tail=4 if reducer is not None else 0)
+            step = collocation_loss_grad_graphed if (USE_CUDA_GRAPHS and M > 0) else collocation_loss_grad
+            ss, flat, vu, vn, _ = step(sol_spec, sol_t, pde_spec, pde_t, m, n, coords,
+                                       M_total=M_total, extra_tail=4 if reducer is not None else 0)
             if reducer is not None:
                 ss = reducer.reduce(flat, ss)
             ctx.save_for_backward(flat)

@@ -314,3 +314,40 @@ def test_unsupported_inputs_fail_loudly():
     bn = Neural_Network(2, 8, 3, 1, Device=DEV, Activation_Function="Tanh", Batch_Norm=True)
     with pytest.raises(NotImplementedError):
         bn(torch.rand(4, 3, device=DEV))
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The CUDA-graph replay of the fused step (functional.USE_CUDA_GRAPHS) gives the same loss and gradients
+    as the eager launches, sees in-place parameter updates, and is rebuilt for a new point count."""
+    from pde_read_b200 import functional as F
+    from pde_read_b200.Loss_Functions import Collocation_Loss
+    su = orc.init_network(3, 30, 2, "Rational", seed=21)
+    sn = orc.init_network(2, 20, 3, "Tanh", seed=22)
+    U, N = make_net(su, "Rational", 2), make_net(sn, "Tanh", 3)
+    params = list(U.parameters()) + list(N.parameters())
+    opt = torch.optim.SGD(params, lr=1e-2)
+
+    def run(P, graphs):
+        F.USE_CUDA_GRAPHS = graphs
+        for p in params:
+            p.grad = None
+        loss = Collocation_Loss(U, N, 1, 2, P, torch.float32, DEV)
+        loss.backward()
+        return loss.item(), [p.grad.clone() for p in params]
+
+    old = F.USE_CUDA_GRAPHS
+    try:
+        for M in (700, 700, 333):
+            P = (torch.rand(M, 2, generator=torch.Generator().manual_seed(M)) * 2 - 1).to(DEV)
+            l0, g0 = run(P, False)
+            l1, g1 = run(P, True)
+            l2, g2 = run(P, True)          # replay
+            # (not bit-equal: the sum of R^2 and the Rational-coefficient sums are combined with atomics)
+            assert abs(l1 - l0) <= 1e-6 * abs(l0) and abs(l2 - l0) <= 1e-6 * abs(l0)
+            for a, b, c in zip(g0, g1, g2):
+                assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-5
+                assert rel_err(c.cpu().numpy(), a.cpu().numpy()) < 1e-5
+            opt.step()                      # in-place update must be visible to the next replay
+    finally:
+        F.USE_CUDA_GRAPHS = old
+        F.release_graphs()
