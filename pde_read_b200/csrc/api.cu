@@ -26,6 +26,12 @@ int block_warps(int W) {
     const int NC = (W + TN - 1) / TN;
     return NC < MAX_WARPS ? NC : MAX_WARPS;
 }
+// Reverse kernel: when the tile's two W x (J*TP) buffers leave room for a single CTA per SM, launch 16 warps
+// -- the products use one warp per neuron chunk, the activation phases (latency-bound) use all of them.
+int bwd_block_warps(int W, int L, int din, int J) {
+    const int nw = block_warps(W);
+    return (bwd_smem_bytes(W, L, din, J) > 112 * 1024 && nw < BWD_WIDE_WARPS) ? BWD_WIDE_WARPS : nw;
+}
 size_t fwd_smem_bytes(int W, int din, int J, int nwarps) {
     const int TP = tile_points(J), HS = h_stride(J);
     return sizeof(float) * ((size_t)2 * W * HS + (size_t)din * TP + (size_t)nwarps * J * TP);

@@ -13,7 +13,8 @@ constexpr int MAXD = PDEREAD_MAX_INPUT_DIM;
 // Thread mapping of the MLP-jet kernels: lane = collocation point, warp = chunk of TN neurons.
 constexpr int TN = 10;          // output neurons per thread in the layer products
 constexpr int TNP = 12;         // chunk length in the packed weights (keeps rows 16-byte aligned)
-constexpr int MAX_WARPS = 12;   // warps per CTA (chunks beyond that are looped over)
+constexpr int MAX_WARPS = 12;   // warps per CTA of the forward kernel (chunks beyond that are looped over)
+constexpr int BWD_WIDE_WARPS = 16;   // warps of the reverse kernel when only one CTA fits an SM
 
 // points per lane as a function of the jet length J = 1 + NX + NT
 #ifndef PDR_PPL_J1
@@ -30,11 +31,12 @@ struct PointsPerLane {
 // Register budget of the CUDA-core kernels.  They are latency-bound in the activation-jet code, so resident
 // warps matter more than registers per thread: the launch bound is only a handle on ptxas' register cap,
 // 65536 / max_threads (blocks are at most MAX_WARPS * 32 threads).  J <= 4: 96 registers -> 4 CTAs of 5 warps
-// per SM at width 50 (tile = 32 points, 53 KB of shared memory); J = 5: 128; J >= 6: 168 (shared memory
-// allows 2 CTAs at most there).  Measured on C2: 2 -> 4 CTAs/SM = 1.29x on the whole step.
+// per SM at width 50 (tile = 32 points, 53 KB of shared memory); J >= 5: 128 (3 CTAs at width 50; wide networks
+// whose tile fills the shared memory of an SM run one CTA of 16 warps instead, see bwd_block_warps).
+// Measured on C2: 2 -> 4 CTAs/SM = 1.29x on the whole step.
 template <int J>
 struct RegCap {
-    static constexpr int max_threads = (J <= 4) ? 640 : (J == 5 ? 512 : 384);
+    static constexpr int max_threads = (J <= 4) ? 640 : 512;
 };
 
 struct NetDev {
@@ -197,6 +199,7 @@ inline int h_stride(int J) { return J * tile_points(J) + 4; }
 size_t fwd_smem_bytes(int W, int din, int J, int nwarps);
 size_t bwd_smem_bytes(int W, int L, int din, int J);
 int block_warps(int W);
+int bwd_block_warps(int W, int L, int din, int J);
 
 void set_last_cuda_error(cudaError_t e);
 void stage_mark(cudaStream_t s);   // measurement hook, see pderead_debug_stage_events

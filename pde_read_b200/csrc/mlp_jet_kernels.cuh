@@ -371,6 +371,11 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
     const int sab = swout + W;                 // rational coefficients [L][7]
     const int NS = sab + 7 * L;
 
+    // activation phases: one work item = G neurons; blocks with more warps than neuron chunks (wide networks,
+    // one CTA per SM) hand out single neurons so that all warps take part
+    const int G = (nwarps > NC) ? 1 : TN;
+    const int nitems = (W + G - 1) / G;
+
     float* gp = a.gpart + (size_t)blockIdx.x * a.lay.total;
     if (!a.accumulate)
         for (int idx = threadIdx.x; idx < a.lay.total; idx += blockDim.x) gp[idx] = 0.f;
@@ -428,27 +433,29 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                 float ab_lo[7];
                 load_ab<ACT>(net, lv, ab_lo);
                 // (a) HP = h^{lv} = act(z^{lv})
-                for (int c = warp; c < NC; c += nwarps) {
+                // (the activation phases hand out single neurons to ALL warps of the block: wide networks that fit one
+                //  CTA per SM launch more warps than the products have neuron chunks, see bwd_block_warps)
+                for (int c = warp; c < nitems; c += nwarps) {
 #pragma unroll 1
-                    for (int n = 0; n < TN; ++n) {
-                        const int i = c * TN + n;
-                        if (i >= W) break;
+                  for (int n = 0; n < G; ++n) {
+                    const int i = c * G + n;
+                    if (i >= W) break;
 #pragma unroll
-                        for (int q = 0; q < PPL; ++q) {
-                            const int pt = q * 32 + lane;
-                            float z[J], y[J];
-                            if (lv == 0) {
-                                input_layer_jet<NX, NT>(net, IN, TP, i, pt, z);
-                            } else {
-                                const float* sp = a.stash + (((size_t)tile * (L - 1) + (lv - 1)) * W + i) * (J * TP) + pt;
+                    for (int q = 0; q < PPL; ++q) {
+                        const int pt = q * 32 + lane;
+                        float z[J], y[J];
+                        if (lv == 0) {
+                            input_layer_jet<NX, NT>(net, IN, TP, i, pt, z);
+                        } else {
+                            const float* sp = a.stash + (((size_t)tile * (L - 1) + (lv - 1)) * W + i) * (J * TP) + pt;
 #pragma unroll
-                                for (int j = 0; j < J; ++j) z[j] = __ldcs(sp + j * TP);
-                            }
-                            act_fwd<ACT, NX, NT, float>(z, ab_lo, y);
-#pragma unroll
-                            for (int j = 0; j < J; ++j) HP[(size_t)i * HS + j * TP + pt] = y[j];
+                            for (int j = 0; j < J; ++j) z[j] = __ldcs(sp + j * TP);
                         }
+                        act_fwd<ACT, NX, NT, float>(z, ab_lo, y);
+#pragma unroll
+                        for (int j = 0; j < J; ++j) HP[(size_t)i * HS + j * TP + pt] = y[j];
                     }
+                  }
                 }
                 __syncthreads();
                 // (b) weight gradient of matrix l:  gW[i][k] += sum_r ZB[i][r] HP[k][r]
@@ -505,10 +512,10 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
             load_ab<ACT>(net, lv, ab);
 #pragma unroll
             for (int t = 0; t < 7; ++t) abbar[t] = 0.f;
-            for (int c = warp; c < NC; c += nwarps) {
+            for (int c = warp; c < nitems; c += nwarps) {
 #pragma unroll 1
-                for (int n = 0; n < TN; ++n) {
-                    const int i = c * TN + n;
+                for (int n = 0; n < G; ++n) {
+                    const int i = c * G + n;
                     if (i >= W) break;
                     const float wo = top ? __ldg(wout + i) : 0.f;
                     float gb = 0.f, gwo = 0.f, gx = 0.f, gt = 0.f;
@@ -654,7 +661,7 @@ int launch_fwd(const FwdArgs& a, cudaStream_t stream) {
 template <int ACT, int NX, int NT>
 int bwd_grid(int W, int L, int din, long long num_tiles, int* grid_out) {
     constexpr int J = 1 + NX + NT;
-    const int nw = block_warps(W);
+    const int nw = bwd_block_warps(W, L, din, J);
     const size_t smem = bwd_smem_bytes(W, L, din, J);
     return grid_for((const void*)mlp_jet_bwd_kernel<ACT, NX, NT>, nw * 32, smem, num_tiles, grid_out);
 }
@@ -662,7 +669,7 @@ int bwd_grid(int W, int L, int din, long long num_tiles, int* grid_out) {
 template <int ACT, int NX, int NT>
 int launch_bwd_impl(const BwdArgs& a, int grid, cudaStream_t stream) {
     constexpr int J = 1 + NX + NT;
-    const int nw = block_warps(a.net.W);
+    const int nw = bwd_block_warps(a.net.W, a.net.L, a.net.din, J);
     const size_t smem = bwd_smem_bytes(a.net.W, a.net.L, a.net.din, J);
     PDR_CUDA_CHECK(cudaFuncSetAttribute((const void*)mlp_jet_bwd_kernel<ACT, NX, NT>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
