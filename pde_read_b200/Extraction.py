@@ -80,11 +80,11 @@ def Generate_Library(
     multi_indices_list).  Dense library for inspection / small M; large extractions should use
     Extract_PDE, which never materialises it."""
     n = int(Spatial_Derivative_Order)
-    su, sn = F.net_spec(Sol_NN), F.net_spec(PDE_NN)
-    tu, tn = F.net_tensors(Sol_NN), F.net_tensors(PDE_NN)
+    su, tu = F.net_spec(Sol_NN), F.net_tensors(Sol_NN)
     # b = N(U, D_x U, ...): the reference computes D_t^m U here too and discards it (:305-344)
     _, Dxn_U = F.sol_derivatives_forward(su, tu, 0, n, Coords)
-    b = F.mlp_forward(sn, tn, Dxn_U)
+    with torch.no_grad():
+        b = PDE_NN(Dxn_U).view(-1)          # Network.forward: input BatchNorm (if any) + fused MLP kernel
     Library = F.library_dense(Dxn_U, n, int(Poly_Degree))
     counts, mi_list = _index_tables(n, int(Poly_Degree))
     return (b.cpu().numpy().astype(np.float32), Library.cpu().numpy().astype(np.float32), counts, mi_list)
@@ -141,9 +141,17 @@ def Extract_PDE(
     With a ``reducer`` (pde_read_b200.parallel.ShardReducer) Coords is this rank's shard and the
     float64 Gram system is all-reduced before the solves."""
     n, K = int(Spatial_Derivative_Order), int(Poly_Degree)
-    su, sn = F.net_spec(Sol_NN), F.net_spec(PDE_NN)
-    tu, tn = F.net_tensors(Sol_NN), F.net_tensors(PDE_NN)
-    G, Atb, btb = F.extraction_gram(su, tu, sn, tn, n, K, Coords)
+    if getattr(PDE_NN, "Batch_Norm", False):
+        # unfused: the input BatchNorm of N sits between the two kernels (statistics over all these points)
+        su, tu = F.net_spec(Sol_NN), F.net_tensors(Sol_NN)
+        _, Dxn_U = F.sol_derivatives_forward(su, tu, 0, n, Coords)
+        with torch.no_grad():
+            b = PDE_NN(Dxn_U).view(-1)
+        G, Atb, btb = F.library_gram(Dxn_U, b, n, K)
+    else:
+        su, sn = F.net_spec(Sol_NN), F.net_spec(PDE_NN)
+        tu, tn = F.net_tensors(Sol_NN), F.net_tensors(PDE_NN)
+        G, Atb, btb = F.extraction_gram(su, tu, sn, tn, n, K, Coords)
     if reducer is not None:
         G, Atb, btb = reducer.reduce_gram(G, Atb, btb)
     X, Res, order, rank, change = F.rfe_gram(G, Atb, btb)

@@ -32,6 +32,11 @@ def Collocation_Loss(
         raise NotImplementedError("the CUDA path computes in float32")
     m = max(int(Time_Derivative_Order), 1)
     n = int(Spatial_Derivative_Order)
+    if getattr(PDE_NN, "Batch_Norm", False):
+        if _reducer is not None:
+            raise NotImplementedError("Batch_Norm=True with sharded points needs synchronised batch statistics")
+        from .PDE_Residual import PDE_Residual
+        return (PDE_Residual(Sol_NN, PDE_NN, m, n, Collocation_Coords, Data_Type, Device) ** 2).mean()
     su, sn = F.net_spec(Sol_NN), F.net_spec(PDE_NN)
     tu, tn = F.net_tensors(Sol_NN), F.net_tensors(PDE_NN)
     return F.CollocationLossFn.apply(Collocation_Coords, su, sn, m, n, len(tu), _reducer, *tu, *tn)

@@ -95,6 +95,10 @@ class Neural_Network(torch.nn.Module):
     def forward(self, X: torch.Tensor) -> torch.Tensor:
         """[B, Input_Dim] -> [B, Output_Dim] (reference Network.py:174-202), evaluated by the fused
         CUDA MLP kernel; differentiable w.r.t. X and the parameters."""
-        spec = F.net_spec(self)
-        out = F.MLPFn.apply(X, spec, *F.net_tensors(self))
+        if self.Batch_Norm:
+            # input normalisation (batch statistics in train mode, running statistics in eval mode, running
+            # statistics updated as a side effect): torch's own BatchNorm1d, exactly the reference's layer
+            X = self.Norm_Layer(X)
+        spec = F.net_spec(self, allow_input_norm=True)
+        out = F.MLPFn.apply(X.contiguous(), spec, *F.net_tensors(self))
         return out.view(-1, 1)

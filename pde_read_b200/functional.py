@@ -32,10 +32,15 @@ class NetSpec:
         return 2 * (self.num_hidden + 1) + (2 * self.num_hidden if self.activation == "Rational" else 0)
 
 
-def net_spec(net) -> NetSpec:
-    """Spec of a pde_read_b200.Network.Neural_Network (or anything with the same attributes)."""
-    if getattr(net, "Batch_Norm", False):
-        raise NotImplementedError("Batch_Norm=True (PDE Network - Normalize Inputs) is not supported by the CUDA path")
+def net_spec(net, allow_input_norm: bool = False) -> NetSpec:
+    """Spec of a pde_read_b200.Network.Neural_Network (or anything with the same attributes).
+
+    The fused kernels evaluate the Linear / activation stack.  A network with ``Batch_Norm=True`` (the
+    reference's "PDE Network - Normalize Inputs", Network.py:100-104,194-195) normalises its INPUTS with a
+    torch BatchNorm1d first; callers that apply that layer themselves pass ``allow_input_norm=True``."""
+    if getattr(net, "Batch_Norm", False) and not allow_input_norm:
+        raise NotImplementedError("this entry point fuses U and N and cannot insert the input BatchNorm of a "
+                                  "Batch_Norm=True network; use the unfused path (Network.forward)")
     if net.Output_Dim != 1:
         raise NotImplementedError("the CUDA path supports Output_Dim == 1 only (got %d)" % net.Output_Dim)
     return NetSpec(net.Num_Hidden_Layers, net.Layers[0].out_features, net.Input_Dim, net.Activation_Name)

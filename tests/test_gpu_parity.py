@@ -313,7 +313,8 @@ def test_unsupported_inputs_fail_loudly():
         Evaluate_Derivatives(net, 1, 2, torch.rand(4, 2, device=DEV), torch.float64, DEV)
     bn = Neural_Network(2, 8, 3, 1, Device=DEV, Activation_Function="Tanh", Batch_Norm=True)
     with pytest.raises(NotImplementedError):
-        bn(torch.rand(4, 3, device=DEV))
+        F.net_spec(bn)                                  # the fused U+N entry points cannot insert the BatchNorm
+    assert bn(torch.rand(4, 3, device=DEV)).shape == (4, 1)
 
 
 def test_cuda_graph_replay_matches_eager():
@@ -351,3 +352,66 @@ def test_cuda_graph_replay_matches_eager():
     finally:
         F.USE_CUDA_GRAPHS = old
         F.release_graphs()
+
+
+def test_pde_network_input_batch_norm_matches_torch_composition():
+    """"PDE Network - Normalize Inputs" (reference Network.py:100-104,194-195): Collocation_Loss + backward with a
+    BatchNorm1d on N's inputs against the same composition in float64 torch (train mode: batch statistics,
+    running statistics updated; eval mode: running statistics)."""
+    from pde_read_b200.Loss_Functions import Collocation_Loss
+    from pde_read_b200.Network import Neural_Network
+    m, n, M = 1, 2, 900
+    su = orc.init_network(3, 24, 2, "Tanh", seed=31)
+    sn = orc.init_network(2, 16, n + 1, "Rational", seed=32)
+    U = make_net(su, "Tanh", 2)
+    N = Neural_Network(2, 16, n + 1, 1, Device=DEV, Activation_Function="Rational", Batch_Norm=True)
+    N.load_state_dict({k: v.to(DEV) for k, v in sn.items()}, strict=False)
+    with torch.no_grad():
+        N.Norm_Layer.weight.copy_(torch.tensor([1.3, 0.7, 1.1], device=DEV))
+        N.Norm_Layer.bias.copy_(torch.tensor([0.1, -0.2, 0.05], device=DEV))
+    P = torch.rand(M, 2, generator=torch.Generator().manual_seed(9)) * 2 - 1
+
+    # float64 composition with the oracle's differentiable pieces
+    S = {k: v.clone().double().requires_grad_(True) for k, v in su.items()}
+    Sn = {k: v.clone().double().requires_grad_(True) for k, v in sn.items()}
+    bw = N.Norm_Layer.weight.detach().cpu().double().requires_grad_(True)
+    bb = N.Norm_Layer.bias.detach().cpu().double().requires_grad_(True)
+    rm, rv = torch.zeros(3, dtype=torch.float64), torch.ones(3, dtype=torch.float64)
+
+    def ref_loss(train):
+        dtm, dxn = orc.evaluate_derivatives(S, "Tanh", m, n, P.double())
+        xn = torch.nn.functional.batch_norm(dxn, rm, rv, bw, bb, training=train, momentum=0.1, eps=1e-5)
+        return ((dtm - orc.network_forward(Sn, "Rational", xn).view(-1)) ** 2).mean()
+
+    N.train()
+    loss = Collocation_Loss(U, N, m, n, P.to(DEV), torch.float32, DEV)
+    loss.backward()
+    want = ref_loss(True)
+    want.backward()
+    assert abs(loss.item() - want.item()) <= 2e-5 * abs(want.item())
+    scale = max(float(v.grad.abs().max()) for v in list(S.values()) + list(Sn.values()))
+
+    def check(g, ref, k):
+        # (the normalisation removes the batch mean, so e.g. dL/d(U's output bias) is exactly zero: compare such
+        #  tensors on the scale of the whole gradient instead of their own)
+        ref = ref.numpy()
+        if np.abs(ref).max() < 1e-6 * scale:
+            assert np.abs(g).max() < 1e-5 * scale, k
+        else:
+            assert rel_err(g, ref) < 2e-4, k
+
+    for k, g in grads_of(U).items():
+        check(g, S[k].grad, k)
+    gN = grads_of(N)
+    for k in sn:
+        check(gN[k], Sn[k].grad, k)
+    check(gN["Norm_Layer.weight"], bw.grad, "Norm_Layer.weight")
+    check(gN["Norm_Layer.bias"], bb.grad, "Norm_Layer.bias")
+    assert rel_err(N.Norm_Layer.running_mean.cpu().numpy(), rm.numpy()) < 1e-5
+    assert rel_err(N.Norm_Layer.running_var.cpu().numpy(), rv.numpy()) < 1e-5
+
+    N.eval()
+    with torch.no_grad():
+        l_eval = Collocation_Loss(U, N, m, n, P.to(DEV), torch.float32, DEV).item()
+    w_eval = ref_loss(False).item()         # (the oracle needs autograd for the derivatives themselves)
+    assert abs(l_eval - w_eval) <= 2e-5 * abs(w_eval)

@@ -169,8 +169,10 @@ def test_product_path_has_no_cpu_fallback():
         Collocation_Loss(U, N, 1, 2, torch.rand(4, 2))
     with pytest.raises(F.PdereadError):
         Generate_Points(np.array([[0.0, 1.0], [0.0, 1.0]]), 10, torch.float32, torch.device("cpu"))
+    bn = Neural_Network(2, 8, 3, 1, Activation_Function="Tanh", Batch_Norm=True)
     with pytest.raises(NotImplementedError):
-        F.net_spec(Neural_Network(2, 8, 3, 1, Activation_Function="Tanh", Batch_Norm=True))
+        F.net_spec(bn)                      # fused U+N entry points refuse a network with input BatchNorm
+    assert F.net_spec(bn, allow_input_norm=True).input_dim == 3
 
 
 def test_library_exports_every_declared_symbol():
