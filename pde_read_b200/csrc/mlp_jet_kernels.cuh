@@ -67,6 +67,41 @@ __device__ __forceinline__ void product_step(float2 (&acc)[PPL][J][TN / 2], cons
         }
 }
 
+// Stash rows keep the J jet coefficients of a point contiguous ([.. neuron][point][jet]) so that one lane moves
+// them with a single 16- / 8-byte access when J is a multiple of 4 / 2 (consecutive lanes -> consecutive addresses).
+template <int J>
+__device__ __forceinline__ void stash_store(float* p, const float* z) {
+    if constexpr (J % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < J; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]);
+    } else if constexpr (J % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < J; j += 2) *reinterpret_cast<float2*>(p + j) = make_float2(z[j], z[j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) p[j] = z[j];
+    }
+}
+template <int J>
+__device__ __forceinline__ void stash_load(const float* p, float* z) {
+    if constexpr (J % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < J; j += 4) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(p + j));
+            z[j] = v.x; z[j + 1] = v.y; z[j + 2] = v.z; z[j + 3] = v.w;
+        }
+    } else if constexpr (J % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < J; j += 2) {
+            const float2 v = __ldcs(reinterpret_cast<const float2*>(p + j));
+            z[j] = v.x; z[j + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) z[j] = __ldcs(p + j);
+    }
+}
+
 // pre-activation jet of hidden layer 0 (the input layer) for neuron i at tile point pt:
 // z_0 = b + sum_d W[i][d] in[d];  the x-series is seeded by input column 1 and the t-series by
 // input column 0 (coords are (t, x), reference PDE_Residual.py:33-34).
@@ -201,9 +236,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
 #pragma unroll
                             for (int j = 0; j < J; ++j) z[j] = acc[q][j][n];
                             if (STASH) {
-                                float* sp = a.stash + (((size_t)tile * (L - 1) + (l - 1)) * W + i) * (J * TP) + pt;
-#pragma unroll
-                                for (int j = 0; j < J; ++j) sp[j * TP] = z[j];
+                                stash_store<J>(a.stash + (((size_t)tile * (L - 1) + (l - 1)) * W + i) * (J * TP) + pt * J, z);
                             }
                             act_fwd<ACT, NX, NT, float>(z, ab, y);
                             if (last) {
@@ -447,9 +480,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                         if (lv == 0) {
                             input_layer_jet<NX, NT>(net, IN, TP, i, pt, z);
                         } else {
-                            const float* sp = a.stash + (((size_t)tile * (L - 1) + (lv - 1)) * W + i) * (J * TP) + pt;
-#pragma unroll
-                            for (int j = 0; j < J; ++j) z[j] = __ldcs(sp + j * TP);
+                            stash_load<J>(a.stash + (((size_t)tile * (L - 1) + (lv - 1)) * W + i) * (J * TP) + pt * J, z);
                         }
                         act_fwd<ACT, NX, NT, float>(z, ab_lo, y);
 #pragma unroll
@@ -529,9 +560,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                         if (lv == 0) {
                             input_layer_jet<NX, NT>(net, IN, TP, i, pt, z);
                         } else {
-                            const float* sp = a.stash + (((size_t)tile * (L - 1) + (lv - 1)) * W + i) * (J * TP) + pt;
-#pragma unroll
-                            for (int j = 0; j < J; ++j) z[j] = __ldcs(sp + j * TP);
+                            stash_load<J>(a.stash + (((size_t)tile * (L - 1) + (lv - 1)) * W + i) * (J * TP) + pt * J, z);
                         }
                         if (top) {
                             float y[J];
