@@ -828,7 +828,13 @@ static int plan_backward_launch(int act, int nx, int nt, BwdPlan& p, BwdArgs b, 
     const int TP = tile_points(jet_len(nx, nt));
     b.wn_packed = p.wn;
     b.num_tiles = (b.M + TP - 1) / TP;
-    b.wg_mode = (b.net.W == 50) ? 1 : 0;
+    {
+        // weight-gradient register tiling: 5x4 or 4x4 outputs per thread, whichever needs fewer (rounds x outputs)
+        const int threads = bwd_block_warps(b.net.W, b.net.L, b.net.din, jet_len(nx, nt)) * 32, W = b.net.W;
+        const int t54 = ((W + 4) / 5) * ((W + 3) / 4), t44 = ((W + 3) / 4) * ((W + 3) / 4);
+        const int c54 = ((t54 + threads - 1) / threads) * 20, c44 = ((t44 + threads - 1) / threads) * 16;
+        b.wg_mode = (c54 <= c44) ? 1 : 0;
+    }
     int g = p.grid;
     if (b.num_tiles < g) g = (int)b.num_tiles;
     if (first) p.grid = g;
