@@ -273,7 +273,7 @@ def residual_forward(sol_spec, sol_tensors, pde_spec, pde_tensors, m: int, n: in
 
 def collocation_loss_grad(sol_spec, sol_tensors, pde_spec, pde_tensors, m: int, n: int, coords: torch.Tensor,
                           M_total: Optional[int] = None, grad_resid: Optional[torch.Tensor] = None,
-                          want_resid: bool = False, extra_tail: int = 0):
+                          want_resid: bool = False, extra_tail: int = 0, private_ws: Optional[list] = None):
     """One fused call: sum(R^2) over these points and d(sum(R^2)/M_total)/d(parameters).
 
     Returns (sum_sq float64[1], flat float32 gradient buffer, sol grad views, pde grad views,
@@ -298,7 +298,13 @@ def collocation_loss_grad(sol_spec, sol_tensors, pde_spec, pde_tensors, m: int, 
             return ss, flat, vu, vn, R
         gr = _check_tensor(grad_resid.reshape(-1), "grad of residual") if grad_resid is not None else None
         nb = lib.pderead_residual_workspace_bytes(ctypes.byref(su), ctypes.byref(sn), m, n, _ws_points(M), 1)
-        ws = workspace(coords.device, nb)
+        if private_ws is not None:
+            # (CUDA-graph capture: the graph keeps raw pointers, so it must not share the growable cached buffer)
+            if not private_ws or private_ws[0].numel() < nb:
+                private_ws[:] = [torch.empty(max(int(nb), 256), dtype=torch.uint8, device=coords.device)]
+            ws = private_ws[0]
+        else:
+            ws = workspace(coords.device, nb)
         _lib.check(lib.pderead_collocation_loss_grad(ctypes.byref(su), ctypes.byref(sn), m, n, coords.data_ptr(), M,
                                                      int(M_total), _ptr(gr), _ptr(R), ss.data_ptr(), ctypes.byref(gu),
                                                      ctypes.byref(gn), 0.0, ws.data_ptr(), ws.numel(), _stream()),
@@ -335,19 +341,21 @@ def collocation_loss_grad_graphed(sol_spec, sol_tensors, pde_spec, pde_tensors, 
         if len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
             _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
         static_coords = coords.clone()
+        own_ws: list = []                                  # workspace owned by this graph (never reallocated)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):                      # warm-up: grows the workspace outside the capture
+        with torch.cuda.stream(side):                      # warm-up: allocates the workspace outside the capture
             for _ in range(2):
                 collocation_loss_grad(sol_spec, sol_tensors, pde_spec, pde_tensors, m, n, static_coords,
-                                      M_total=M_total, extra_tail=extra_tail)
+                                      M_total=M_total, extra_tail=extra_tail, private_ws=own_ws)
         torch.cuda.current_stream(dev).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             ss, flat, vu, vn, _ = collocation_loss_grad(sol_spec, sol_tensors, pde_spec, pde_tensors, m, n,
-                                                        static_coords, M_total=M_total, extra_tail=extra_tail)
+                                                        static_coords, M_total=M_total, extra_tail=extra_tail,
+                                                        private_ws=own_ws)
         ent = (graph, static_coords, ss, flat, [tuple(v.shape) for v in vu], [tuple(v.shape) for v in vn],
-               list(sol_tensors) + list(pde_tensors))      # keep the parameter tensors alive with the graph
+               list(sol_tensors) + list(pde_tensors) + own_ws)   # keep parameters and workspace alive with the graph
         _GRAPH_CACHE[key] = ent
     graph, static_coords, ss, flat, shu, shn, _keep = ent
     static_coords.copy_(coords)
