@@ -417,6 +417,16 @@ def main():
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                 "stage_ms": [float(v) for v in stage_ms]}
 
+    # the two standard rooflines, for context (neither binds: 12 algorithmic bytes and ~3e5 fp32 FLOP per point,
+    # with 3xTF32 accuracy too low for the gradient path -- DESIGN.md section 4)
+    mp = measured_peaks()
+    step_flops = (3.0 * (FU + FN) if not c.get("extraction") else float(FU + FN)) * M_local / (ms_per_step * 1e-3)
+    step_bytes = (12.0 if not c.get("extraction") else 8.0) * M_local / (ms_per_step * 1e-3)
+    roof["bound_note"] = ("kernel is bound by FP32 FMA issue on the CUDA cores; whole step = %.4f of the measured HBM peak "
+                          "(%.1f GB/s) on algorithmic bytes and %.4f of the measured bf16 tensor peak (%.1f TFLOP/s) on "
+                          "algorithmic FLOPs" % (step_bytes / 1e9 / mp.get("hbm_gbs", 6538.9), mp.get("hbm_gbs", 6538.9),
+                                                 step_flops / 1e12 / mp.get("bf16_tflops", 1650.7), mp.get("bf16_tflops", 1650.7)))
+
     # ------------------------------------------------ CPU baseline beside it (bounded sample)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
