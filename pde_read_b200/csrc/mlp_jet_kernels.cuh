@@ -463,32 +463,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
             const bool top = (lv == L - 1);
             if (!top) {
                 const int l = lv + 1;   // weight matrix between hidden layers lv and lv+1
-                float ab_lo[7];
-                load_ab<ACT>(net, lv, ab_lo);
-                // (a) HP = h^{lv} = act(z^{lv})
-                // (the activation phases hand out single neurons to ALL warps of the block: wide networks that fit one
-                //  CTA per SM launch more warps than the products have neuron chunks, see bwd_block_warps)
-                for (int c = warp; c < nitems; c += nwarps) {
-#pragma unroll 1
-                  for (int n = 0; n < G; ++n) {
-                    const int i = c * G + n;
-                    if (i >= W) break;
-#pragma unroll
-                    for (int q = 0; q < PPL; ++q) {
-                        const int pt = q * 32 + lane;
-                        float z[J], y[J];
-                        if (lv == 0) {
-                            input_layer_jet<NX, NT>(net, IN, TP, i, pt, z);
-                        } else {
-                            stash_load<J>(a.stash + (((size_t)tile * (L - 1) + (lv - 1)) * W + i) * (J * TP) + pt * J, z);
-                        }
-                        act_fwd<ACT, NX, NT, float>(z, ab_lo, y);
-#pragma unroll
-                        for (int j = 0; j < J; ++j) HP[(size_t)i * HS + j * TP + pt] = y[j];
-                    }
-                  }
-                }
-                __syncthreads();
+                // HP holds h^{lv} = act(z^{lv}): written by phase (d) of the iteration above (see there)
                 // (b) weight gradient of matrix l:  gW[i][k] += sum_r ZB[i][r] HP[k][r]
                 {
                     float* gw = gp + a.lay.off_w[l];
@@ -538,9 +513,13 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                 __syncthreads();
             }
 
-            // (d) VJP of the activation of hidden layer lv:  ZB = zbar^{lv}
-            float ab[7], abbar[7];
+            // (d) VJP of the activation of hidden layer lv:  ZB = zbar^{lv}.  The same pass re-evaluates the
+            //     activations of the layer below, HP = h^{lv-1} = act(z^{lv-1}), which the next iteration's weight
+            //     gradient needs: an independent dependency chain in the same loop (each thread overwrites the
+            //     hbar element it has just read).
+            float ab[7], ab_lo[7], abbar[7];
             load_ab<ACT>(net, lv, ab);
+            load_ab<ACT>(net, lv > 0 ? lv - 1 : 0, ab_lo);
 #pragma unroll
             for (int t = 0; t < 7; ++t) abbar[t] = 0.f;
             for (int c = warp; c < nitems; c += nwarps) {
@@ -574,6 +553,17 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                         } else {
 #pragma unroll
                             for (int j = 0; j < J; ++j) ybar[j] = HP[(size_t)i * HS + j * TP + pt];
+                        }
+                        if (lv > 0) {
+                            float zl[J], yl[J];
+                            if (lv == 1) {
+                                input_layer_jet<NX, NT>(net, IN, TP, i, pt, zl);
+                            } else {
+                                stash_load<J>(a.stash + (((size_t)tile * (L - 1) + (lv - 2)) * W + i) * (J * TP) + pt * J, zl);
+                            }
+                            act_fwd<ACT, NX, NT, float>(zl, ab_lo, yl);
+#pragma unroll
+                            for (int j = 0; j < J; ++j) HP[(size_t)i * HS + j * TP + pt] = yl[j];
                         }
                         act_vjp<ACT, NX, NT, float>(z, ab, ybar, zbar, abbar);
 #pragma unroll
