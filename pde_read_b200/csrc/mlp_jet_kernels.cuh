@@ -645,14 +645,31 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
 // =============================================================================================
 // launchers
 // =============================================================================================
+// Resident CTAs for (kernel, block, shared memory) on the current device: attribute + occupancy queries cost
+// several microseconds each, a step launches four such kernels, so the answer is remembered per thread.
 inline int grid_for(const void* kernel, int threads, size_t smem, long long num_tiles, int* grid_out) {
-    int dev = 0, sms = 0, occ = 0;
+    struct Entry { const void* k; int threads; size_t smem; int dev; long long resident; };
+    static thread_local Entry cache[16];
+    static thread_local int used = 0;
+    int dev = 0;
     PDR_CUDA_CHECK(cudaGetDevice(&dev));
-    PDR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    PDR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PDR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
-    if (occ < 1) return PDEREAD_ERR_UNSUPPORTED_NET;
-    long long g = (long long)sms * occ;
+    long long resident = -1;
+    for (int i = 0; i < used; ++i)
+        if (cache[i].k == kernel && cache[i].threads == threads && cache[i].smem == smem && cache[i].dev == dev) {
+            resident = cache[i].resident;
+            break;
+        }
+    if (resident < 0) {
+        int sms = 0, occ = 0;
+        PDR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        PDR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PDR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+        if (occ < 1) return PDEREAD_ERR_UNSUPPORTED_NET;
+        resident = (long long)sms * occ;
+        const int slot = used < 16 ? used++ : 0;
+        cache[slot] = Entry{kernel, threads, smem, dev, resident};
+    }
+    long long g = resident;
     if (g > num_tiles) g = num_tiles;
     if (g < 1) g = 1;
     *grid_out = (int)g;
@@ -690,8 +707,7 @@ int launch_bwd_impl(const BwdArgs& a, int grid, cudaStream_t stream) {
     constexpr int J = 1 + NX + NT;
     const int nw = bwd_block_warps(a.net.W, a.net.L, a.net.din, J);
     const size_t smem = bwd_smem_bytes(a.net.W, a.net.L, a.net.din, J);
-    PDR_CUDA_CHECK(cudaFuncSetAttribute((const void*)mlp_jet_bwd_kernel<ACT, NX, NT>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (the dynamic shared-memory attribute was set by bwd_grid -> grid_for for this shape)
     mlp_jet_bwd_kernel<ACT, NX, NT><<<grid, nw * 32, smem, stream>>>(a);
     PDR_CUDA_CHECK(cudaGetLastError());
     return PDEREAD_OK;

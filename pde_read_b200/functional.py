@@ -66,7 +66,24 @@ def _check_tensor(t: torch.Tensor, what: str, dtype=torch.float32) -> torch.Tens
     return t.contiguous()
 
 
+_NET_CACHE: dict = {}
+
+
 def _fill_net(spec: NetSpec, tensors: Sequence[torch.Tensor]) -> Tuple[pderead_net, list]:
+    """ctypes description of a network.  Building it touches every parameter tensor, so the result is cached by
+    (spec, device pointers): optimisers update parameters in place and a training loop hits the cache every step."""
+    key = (spec, tuple([t.data_ptr() for t in tensors]))
+    hit = _NET_CACHE.get(key)
+    if hit is not None:
+        return hit
+    out = _fill_net_uncached(spec, tensors)
+    if len(_NET_CACHE) > 64:
+        _NET_CACHE.clear()
+    _NET_CACHE[key] = out
+    return out
+
+
+def _fill_net_uncached(spec: NetSpec, tensors: Sequence[torch.Tensor]) -> Tuple[pderead_net, list]:
     if len(tensors) != spec.num_tensors:
         raise PdereadError("expected %d parameter tensors, got %d" % (spec.num_tensors, len(tensors)))
     if spec.num_hidden < 1 or spec.num_hidden > _lib.MAX_HIDDEN_LAYERS:
@@ -100,28 +117,66 @@ def _fill_net(spec: NetSpec, tensors: Sequence[torch.Tensor]) -> Tuple[pderead_n
     return s, keep
 
 
+class _LazyViews:
+    """The per-parameter gradient views of a flat buffer, created on first use (a training step only needs
+    the flat buffer; creating 32 view tensors per call costs more host time than launching the kernels)."""
+
+    def __init__(self, flat: torch.Tensor, layout):
+        self._flat, self._layout, self._views = flat, layout, None
+
+    def _make(self):
+        if self._views is None:
+            self._views = [self._flat.as_strided(shape, stride, off) for (off, shape, stride) in self._layout]
+        return self._views
+
+    def __iter__(self):
+        return iter(self._make())
+
+    def __len__(self):
+        return len(self._layout)
+
+    def __getitem__(self, i):
+        return self._make()[i]
+
+    def __add__(self, other):
+        return list(self) + list(other)
+
+    def __radd__(self, other):
+        return list(other) + list(self)
+
+
+def _contig_strides(shape):
+    st, acc = [], 1
+    for d in reversed(shape):
+        st.append(acc)
+        acc *= d
+    return tuple(reversed(st))
+
+
 def _grad_views(spec: NetSpec, tensors: Sequence[torch.Tensor], flat: torch.Tensor, offset: int = 0
-                ) -> Tuple[pderead_net_grad, List[torch.Tensor], int]:
-    """Carve one gradient view per parameter tensor out of `flat` (float32, device) starting at
-    `offset` (every view 16-byte aligned) and point a pderead_net_grad at them."""
+                ) -> Tuple[pderead_net_grad, "_LazyViews", int]:
+    """One gradient slot per parameter tensor inside `flat` (float32, device) starting at `offset` (every slot
+    16-byte aligned); a pderead_net_grad pointing at the slots and lazily created views of them."""
     g = pderead_net_grad()
-    views: List[torch.Tensor] = []
     L = spec.num_hidden
+    base_ptr = flat.data_ptr()
     off = offset
-    for idx, t in enumerate(tensors):
+    ptrs, layout = [], []
+    for t in tensors:
+        shape = tuple(t.shape)
         n = t.numel()
-        v = flat[off:off + n].view(t.shape)
-        views.append(v)
+        ptrs.append(base_ptr + 4 * off)
+        layout.append((off, shape, _contig_strides(shape)))
         off += (n + 3) // 4 * 4
     for i in range(L + 1):
-        g.weight[i] = views[2 * i].data_ptr()
-        g.bias[i] = views[2 * i + 1].data_ptr()
+        g.weight[i] = ptrs[2 * i]
+        g.bias[i] = ptrs[2 * i + 1]
     if spec.activation == "Rational":
-        base = 2 * (L + 1)
+        b0 = 2 * (L + 1)
         for i in range(L):
-            g.rat_a[i] = views[base + 2 * i].data_ptr()
-            g.rat_b[i] = views[base + 2 * i + 1].data_ptr()
-    return g, views, off
+            g.rat_a[i] = ptrs[b0 + 2 * i]
+            g.rat_b[i] = ptrs[b0 + 2 * i + 1]
+    return g, _LazyViews(flat, layout), off
 
 
 def flat_grad_numel(tensors: Sequence[torch.Tensor]) -> int:
@@ -475,7 +530,7 @@ class CollocationLossFn(torch.autograd.Function):
             numel = 1
             for d in shape:
                 numel *= d
-            grads.append(scaled[off:off + numel].view(shape) if f else None)
+            grads.append(scaled.as_strided(shape, _contig_strides(shape), off) if f else None)
             off += (numel + 3) // 4 * 4
         return (None, None, None, None, None, None, None, *grads)
 
