@@ -75,6 +75,8 @@ const char* pderead_version(void);
 const char* pderead_status_string(int status);
 /* cudaError_t of the most recent failing CUDA call on this host thread (diagnostic only). */
 int pderead_last_cuda_error(void);
+/* "<source file>:<line>: <cudaGetErrorString>" of the CUDA call that failed last on this thread ("" if none). */
+const char* pderead_last_cuda_error_where(void);
 
 /* ---- Evaluate_Derivatives: reference PDE_Residual.py:9-147 ------------------------------------
  * d_coords [M,2] (col 0 = t, col 1 = x) -> d_dtm [M] = D_t^m U, d_dxn [M, n+1] = D_x^k U, k=0..n.

@@ -3,10 +3,12 @@ Code/Test_Train.py:10-20 and :109-118).  The closure is where Loss.backward() tr
 kernels; it works unchanged under Adam, SGD and LBFGS (which calls it several times per step)."""
 from __future__ import annotations
 
+import os
 from typing import Tuple
 
 import torch
 
+from . import functional as F
 from .Loss_Functions import Collocation_Loss, Data_Loss
 from .Network import Neural_Network
 
@@ -25,10 +27,14 @@ def Discovery_Training(
     """One epoch: a single Optimizer.step over loss = Collocation_Loss + Data_Loss."""
     Sol_NN.train()
     PDE_NN.train()
+    fast = _fast_closure_ok(Sol_NN, PDE_NN, Collocation_Coords, Data_Coords, Data_Type)
 
     def Discovery_Closure():
         if torch.is_grad_enabled():
             Optimizer.zero_grad()
+        if fast and torch.is_grad_enabled():
+            return _fused_closure(Sol_NN, PDE_NN, max(int(Time_Derivative_Order), 1), int(Spatial_Derivative_Order),
+                                  Collocation_Coords, Data_Coords, Data_Values)
         Loss = (Collocation_Loss(Sol_NN, PDE_NN, Time_Derivative_Order, Spatial_Derivative_Order, Collocation_Coords,
                                  Data_Type, Device)
                 + Data_Loss(Sol_NN, Data_Coords, Data_Values, Data_Type, Device))
@@ -37,6 +43,44 @@ def Discovery_Training(
         return Loss
 
     Optimizer.step(Discovery_Closure)
+
+
+# The closure above is what the reference runs (Test_Train.py:73-102).  With ~50 small parameter tensors the
+# autograd bookkeeping around the two fused kernels costs more host time than the kernels take at the
+# reference's default 5000 points, so when nothing needs the graph (plain training: every parameter trainable,
+# no input BatchNorm, no point sharding) the same numbers are produced without it: the collocation call returns
+# d(mean R^2)/d(theta) for both networks in one flat buffer, the data term's reverse kernel ADDS into U's slots
+# of that buffer, and the parameters' .grad become views of it.  PDEREAD_FAST_CLOSURE=0 keeps the autograd path.
+_FAST_CLOSURE = os.environ.get("PDEREAD_FAST_CLOSURE", "1") not in ("0", "", "off")
+
+
+def _fast_closure_ok(Sol_NN, PDE_NN, Collocation_Coords, Data_Coords, Data_Type) -> bool:
+    from . import Loss_Functions
+    if not _FAST_CLOSURE or Loss_Functions._reducer is not None or Data_Type != torch.float32:
+        return False
+    if getattr(Sol_NN, "Batch_Norm", False) or getattr(PDE_NN, "Batch_Norm", False):
+        return False
+    if not (Collocation_Coords.is_cuda and Data_Coords.is_cuda) or Collocation_Coords.shape[0] == 0 or Data_Coords.shape[0] == 0:
+        return False
+    return all(p.requires_grad for p in list(Sol_NN.parameters()) + list(PDE_NN.parameters()))
+
+
+def _fused_closure(Sol_NN, PDE_NN, m, n, Collocation_Coords, Data_Coords, Data_Values) -> torch.Tensor:
+    su, sn = F.net_spec(Sol_NN), F.net_spec(PDE_NN)
+    tu, tn = F.net_tensors(Sol_NN), F.net_tensors(PDE_NN)
+    ss, flat, vu, vn, _ = F.collocation_loss_grad(su, tu, sn, tn, m, n, Collocation_Coords)
+    Coll = ss.reshape(()) / float(Collocation_Coords.shape[0])
+    # data term: mean((U(x) - u)^2) (reference Loss_Functions.py:115-122; float64 targets promote the loss)
+    u = F.mlp_forward(su, tu, Data_Coords)
+    diff = u - Data_Values.reshape(-1)
+    Data = (diff ** 2).mean()
+    F.mlp_backward_accumulate(su, tu, Data_Coords, (diff * (2.0 / diff.numel())).to(torch.float32), flat, 0)
+    for p, g in zip(tu + tn, list(vu) + list(vn)):
+        if p.grad is None:
+            p.grad = g
+        else:
+            p.grad.add_(g)
+    return (Coll.to(Data.dtype) + Data).detach()
 
 
 def Discovery_Testing(

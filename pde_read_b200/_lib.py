@@ -56,6 +56,7 @@ PROTOTYPES = {
     "pderead_version": (c_char_p, []),
     "pderead_status_string": (c_char_p, [c_int]),
     "pderead_last_cuda_error": (c_int, []),
+    "pderead_last_cuda_error_where": (ctypes.c_char_p, []),
     "pderead_sol_derivatives_workspace_bytes": (c_size_t, [_NET, c_int, c_int, c_int64, c_int]),
     "pderead_sol_derivatives_forward": (c_int, [_NET, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                                 c_size_t, c_void_p]),
@@ -117,5 +118,6 @@ def check(rc: int, what: str = "") -> None:
         lib = load()
         msg = lib.pderead_status_string(rc).decode()
         if rc == -5:
-            msg += " (cudaError %d)" % lib.pderead_last_cuda_error()
+            msg += " (cudaError %d at %s)" % (lib.pderead_last_cuda_error(),
+                                               (lib.pderead_last_cuda_error_where() or b"?").decode())
         raise PdereadError("%s failed: %s [%d]" % (what or "pderead call", msg, rc))

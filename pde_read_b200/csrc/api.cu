@@ -3,7 +3,10 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <mutex>
 
 #include "internal.h"
 #include "umma.cuh"
@@ -11,11 +14,48 @@
 namespace pdr {
 
 static thread_local int g_last_cuda_error = 0;
-void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = (int)e; }
+static thread_local char g_last_cuda_where[160] = "";
+void set_last_cuda_error(cudaError_t e, const char* file, int line) {
+    g_last_cuda_error = (int)e;
+    const char* base = file;
+    for (const char* p = file; *p; ++p)
+        if (*p == '/') base = p + 1;
+    snprintf(g_last_cuda_where, sizeof(g_last_cuda_where), "%s:%d: %s", base, line, cudaGetErrorString(e));
+    (void)cudaGetLastError();      // clear the non-sticky error so that the next call starts clean
+}
 
 // Optional measurement hook (bench.py): a caller-owned array of cudaEvent_t that the next calls on
 // this host thread record, one after every kernel launch, so individual kernels can be timed
 // inside an otherwise unmodified step without synchronising.
+int ensure_dynamic_smem(const void* kernel, size_t smem) {
+    struct Limit { const void* k; int dev; size_t smem; };
+    constexpr int NLIMIT = 256;                  // > number of kernel instantiations x devices of one node in practice
+    static Limit limits[NLIMIT];
+    static int nlimits = 0;
+    static std::mutex mu;
+    int dev = 0;
+    PDR_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    Limit* lim = nullptr;
+    for (int i = 0; i < nlimits; ++i)
+        if (limits[i].k == kernel && limits[i].dev == dev) {
+            lim = &limits[i];
+            break;
+        }
+    if (lim != nullptr && smem <= lim->smem) return PDEREAD_OK;
+    if (lim == nullptr && nlimits == NLIMIT) {
+        // table full: set the device maximum once for kernels that do not fit (never lowers anything)
+        int optin = 0;
+        PDR_CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        PDR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        return PDEREAD_OK;
+    }
+    PDR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (lim != nullptr) lim->smem = smem;
+    else limits[nlimits++] = Limit{kernel, dev, smem};
+    return PDEREAD_OK;
+}
+
 static thread_local cudaEvent_t* g_stage_events = nullptr;
 static thread_local int g_stage_count = 0, g_stage_next = 0;
 void stage_mark(cudaStream_t s) {
@@ -682,6 +722,7 @@ const char* pderead_status_string(int status) {
 }
 
 int pderead_last_cuda_error(void) { return g_last_cuda_error; }
+const char* pderead_last_cuda_error_where(void) { return pdr::g_last_cuda_where; }
 
 int pderead_debug_stage_events(void* const* events, int count) {
     g_stage_events = (cudaEvent_t*)events;

@@ -227,10 +227,10 @@ int gram_launch(const LibTable& t, bool dense, const float* src, const float* b,
     const size_t smem = gram_smem_bytes(t);
     dim3 grid((unsigned)slices, (unsigned)npairs);
     if (dense) {
-        PDR_CUDA_CHECK(cudaFuncSetAttribute((const void*)gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { const int rc_ = ensure_dynamic_smem((const void*)gram_kernel<true>, smem); if (rc_ != PDEREAD_OK) return rc_; }
         gram_kernel<true><<<grid, 256, smem, s>>>(t, src, b, M, nblk, G, Atb, btb);
     } else {
-        PDR_CUDA_CHECK(cudaFuncSetAttribute((const void*)gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { const int rc_ = ensure_dynamic_smem((const void*)gram_kernel<false>, smem); if (rc_ != PDEREAD_OK) return rc_; }
         gram_kernel<false><<<grid, 256, smem, s>>>(t, src, b, M, nblk, G, Atb, btb);
     }
     PDR_CUDA_CHECK(cudaGetLastError());
@@ -407,7 +407,7 @@ int pderead_library_dense(const float* d_dxn, int64_t M, int n, int K, float* d_
     if (M < 0 || (M > 0 && (!d_dxn || !d_library))) return PDEREAD_ERR_BAD_ARGUMENT;
     if (M == 0) return PDEREAD_OK;
     const size_t smem = sizeof(float) * ((size_t)(t.n + 1) * GP + GP + (size_t)t.C * GP);
-    PDR_CUDA_CHECK(cudaFuncSetAttribute((const void*)library_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int rc_ = ensure_dynamic_smem((const void*)library_dense_kernel, smem); if (rc_ != PDEREAD_OK) return rc_; }
     const long long tiles = (M + GP - 1) / GP;
     library_dense_kernel<<<(int)(tiles < 1184 ? tiles : 1184), 256, smem, (cudaStream_t)stream>>>(t, d_dxn, M, d_library);
     PDR_CUDA_CHECK(cudaGetLastError());
@@ -447,7 +447,7 @@ int pderead_rfe_gram(const double* d_G, const double* d_Atb, const double* d_btb
     const int use_smem = (small + mat + 1024 <= (size_t)maxsm) ? 1 : 0;
     if (!use_smem && (!ws || ws_bytes < mat)) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
     const size_t smem = use_smem ? small + mat : small;
-    PDR_CUDA_CHECK(cudaFuncSetAttribute((const void*)rfe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int rc_ = ensure_dynamic_smem((const void*)rfe_kernel, smem); if (rc_ != PDEREAD_OK) return rc_; }
     rfe_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(d_G, d_Atb, d_btb, C, d_X, d_residual, d_order, d_rank, d_change,
                                                         (double*)ws, use_smem);
     PDR_CUDA_CHECK(cudaGetLastError());

@@ -201,7 +201,11 @@ size_t bwd_smem_bytes(int W, int L, int din, int J);
 int block_warps(int W);
 int bwd_block_warps(int W, int L, int din, int J);
 
-void set_last_cuda_error(cudaError_t e);
+void set_last_cuda_error(cudaError_t e, const char* file, int line);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is one number per (kernel, device) for the whole process while one
+// kernel serves several network shapes from several threads (autograd runs reverse calls on its own): this
+// only ever raises it, so a shape seen earlier can always be launched again.
+int ensure_dynamic_smem(const void* kernel, size_t smem);
 void stage_mark(cudaStream_t s);   // measurement hook, see pderead_debug_stage_events
 
 // extraction.cu
@@ -214,7 +218,7 @@ int library_gram_launch(const float* dxn, const float* b, long long M, int n, in
     do {                                                  \
         cudaError_t _e = (expr);                          \
         if (_e != cudaSuccess) {                          \
-            pdr::set_last_cuda_error(_e);                 \
+            pdr::set_last_cuda_error(_e, __FILE__, __LINE__); \
             return PDEREAD_ERR_CUDA;                      \
         }                                                 \
     } while (0)

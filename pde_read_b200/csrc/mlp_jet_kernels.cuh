@@ -19,6 +19,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include "internal.h"
 #include "jet_math.cuh"
 
@@ -646,13 +648,17 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
 // launchers
 // =============================================================================================
 // Resident CTAs for (kernel, block, shared memory) on the current device: attribute + occupancy queries cost
-// several microseconds each, a step launches four such kernels, so the answer is remembered per thread.
+// several microseconds each, a step launches four such kernels, so the answer is remembered.
 inline int grid_for(const void* kernel, int threads, size_t smem, long long num_tiles, int* grid_out) {
     struct Entry { const void* k; int threads; size_t smem; int dev; long long resident; };
-    static thread_local Entry cache[16];
-    static thread_local int used = 0;
+    constexpr int NCACHE = 32;
+    // process-wide, like the attribute: autograd runs the reverse calls on its own thread
+    static Entry cache[NCACHE];
+    static int used = 0, next_slot = 0;
+    static std::mutex mu;
     int dev = 0;
     PDR_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
     long long resident = -1;
     for (int i = 0; i < used; ++i)
         if (cache[i].k == kernel && cache[i].threads == threads && cache[i].smem == smem && cache[i].dev == dev) {
@@ -662,11 +668,12 @@ inline int grid_for(const void* kernel, int threads, size_t smem, long long num_
     if (resident < 0) {
         int sms = 0, occ = 0;
         PDR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        PDR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int rc = ensure_dynamic_smem(kernel, smem);
+        if (rc != PDEREAD_OK) return rc;
         PDR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
         if (occ < 1) return PDEREAD_ERR_UNSUPPORTED_NET;
         resident = (long long)sms * occ;
-        const int slot = used < 16 ? used++ : 0;
+        const int slot = used < NCACHE ? used++ : (next_slot++ % NCACHE);
         cache[slot] = Entry{kernel, threads, smem, dev, resident};
     }
     long long g = resident;

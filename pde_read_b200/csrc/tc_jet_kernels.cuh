@@ -793,8 +793,8 @@ int launch_tc_fwd(const TcFwdArgs& a, cudaStream_t stream) {
     const size_t smem = a.geom.smem_bytes;
 #define PDR_TC_LAUNCH(MR, ST)                                                                                            \
     do {                                                                                                                 \
-        PDR_CUDA_CHECK(cudaFuncSetAttribute((const void*)tc_jet_fwd_kernel<ACT, NX, NT, MR, ST>,                        \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+        const int rc_ = ensure_dynamic_smem((const void*)tc_jet_fwd_kernel<ACT, NX, NT, MR, ST>, smem);                  \
+        if (rc_ != PDEREAD_OK) return rc_;                                                                               \
         tc_jet_fwd_kernel<ACT, NX, NT, MR, ST><<<(int)grid, TC_THREADS, smem, stream>>>(a);                              \
     } while (0)
     if (a.geom.mrows == 64) {
@@ -811,12 +811,12 @@ template <int ACT, int NX, int NT>
 int launch_tc_bwd(const TcBwdArgs& a, int grid, cudaStream_t stream) {
     const size_t smem = a.geom.smem_bytes;
     if (a.geom.mrows == 64) {
-        PDR_CUDA_CHECK(cudaFuncSetAttribute((const void*)tc_jet_bwd_kernel<ACT, NX, NT, 64>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int rc = ensure_dynamic_smem((const void*)tc_jet_bwd_kernel<ACT, NX, NT, 64>, smem);
+        if (rc != PDEREAD_OK) return rc;
         tc_jet_bwd_kernel<ACT, NX, NT, 64><<<grid, TC_THREADS, smem, stream>>>(a);
     } else {
-        PDR_CUDA_CHECK(cudaFuncSetAttribute((const void*)tc_jet_bwd_kernel<ACT, NX, NT, 128>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int rc = ensure_dynamic_smem((const void*)tc_jet_bwd_kernel<ACT, NX, NT, 128>, smem);
+        if (rc != PDEREAD_OK) return rc;
         tc_jet_bwd_kernel<ACT, NX, NT, 128><<<grid, TC_THREADS, smem, stream>>>(a);
     }
     PDR_CUDA_CHECK(cudaGetLastError());

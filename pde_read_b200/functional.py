@@ -305,6 +305,25 @@ def mlp_backward(spec: NetSpec, tensors, X: torch.Tensor, grad_out: torch.Tensor
     return gin, views
 
 
+def mlp_backward_accumulate(spec: NetSpec, tensors, X: torch.Tensor, grad_out: torch.Tensor, flat: torch.Tensor,
+                            offset: int = 0) -> None:
+    """Reverse pass of the plain MLP whose parameter gradients are ADDED (beta = 1) to the slots of this network
+    inside an existing flat gradient buffer (layout of _grad_views at `offset`)."""
+    lib = _lib.load()
+    X = _check_tensor(X.detach(), "network input")
+    M = X.shape[0]
+    if M == 0:
+        return
+    with torch.cuda.device(X.device):
+        s, keep = _fill_net(spec, tensors)
+        g, _, _ = _grad_views(spec, tensors, flat, offset)
+        go = _check_tensor(grad_out.reshape(-1), "grad of network output")
+        nb = lib.pderead_mlp_workspace_bytes(ctypes.byref(s), _ws_points(M), 1)
+        ws = workspace(X.device, nb)
+        _lib.check(lib.pderead_mlp_backward(ctypes.byref(s), X.data_ptr(), M, go.data_ptr(), None, ctypes.byref(g),
+                                            1.0, ws.data_ptr(), ws.numel(), _stream()), "pderead_mlp_backward")
+
+
 def residual_forward(sol_spec, sol_tensors, pde_spec, pde_tensors, m: int, n: int, coords: torch.Tensor,
                      want_resid: bool = True) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
     """-> (R [M] or None, sum(R^2) as a float64 device scalar)."""

@@ -415,3 +415,60 @@ def test_pde_network_input_batch_norm_matches_torch_composition():
         l_eval = Collocation_Loss(U, N, m, n, P.to(DEV), torch.float32, DEV).item()
     w_eval = ref_loss(False).item()         # (the oracle needs autograd for the derivatives themselves)
     assert abs(l_eval - w_eval) <= 2e-5 * abs(w_eval)
+
+
+def test_fused_training_closure_matches_autograd_closure():
+    """Discovery_Training's graph-free closure (collocation gradients + data-term gradients accumulated by the
+    kernels into one flat buffer) leaves the same .grad and takes the same optimiser step as the reference-style
+    autograd closure, for Adam and for LBFGS (which re-enters the closure)."""
+    import copy
+    from pde_read_b200 import Test_Train
+    su = orc.init_network(3, 30, 2, "Rational", seed=41)
+    sn = orc.init_network(2, 20, 3, "Tanh", seed=42)
+    gen = torch.Generator().manual_seed(43)
+    P = (torch.rand(1500, 2, generator=gen) * 2 - 1).to(DEV)
+    Xd = (torch.rand(700, 2, generator=gen) * 2 - 1).to(DEV)
+    yd = torch.sin(Xd[:, 1].double()) * torch.exp(-Xd[:, 0].double())        # float64 targets, as in the shipped npz
+    old = Test_Train._FAST_CLOSURE
+    try:
+        for opt_name in ("Adam", "LBFGS"):
+            results = []
+            for fast in (False, True):
+                Test_Train._FAST_CLOSURE = fast
+                U, N = make_net(su, "Rational", 2), make_net(sn, "Tanh", 3)
+                params = list(U.parameters()) + list(N.parameters())
+                opt = (torch.optim.Adam(params, lr=1e-3) if opt_name == "Adam"
+                       else torch.optim.LBFGS(params, lr=0.1, max_iter=4))
+                for _ in range(3):
+                    Test_Train.Discovery_Training(U, N, 1, 2, P, Xd, yd, opt, torch.float32, DEV)
+                results.append(([p.detach().clone() for p in params], [p.grad.detach().clone() for p in params]))
+            for a, b in zip(results[0][0], results[1][0]):
+                assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < (2e-5 if opt_name == "Adam" else 2e-3)
+            for a, b in zip(results[0][1], results[1][1]):
+                assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < (1e-4 if opt_name == "Adam" else 5e-2)
+    finally:
+        Test_Train._FAST_CLOSURE = old
+
+
+def test_one_kernel_alternating_between_network_shapes():
+    """The J = 1 kernels serve every network of an activation family; launching a wide, a narrow and the wide
+    network again must work (the per-kernel dynamic shared-memory limit is only ever raised)."""
+    from pde_read_b200 import functional as F
+    wide = make_net(orc.init_network(2, 100, 3, "Rational", seed=5), "Rational", 3)
+    narrow = make_net(orc.init_network(2, 12, 3, "Rational", seed=6), "Rational", 3)
+    X = torch.rand(4000, 3, device=DEV)
+    go = torch.ones(4000, device=DEV)
+    first = None
+    for net in (wide, narrow, wide, narrow, wide):
+        spec, t = F.net_spec(net), F.net_tensors(net)
+        y = F.mlp_forward(spec, t, X)
+        _, views = F.mlp_backward(spec, t, X, go, False)
+        torch.cuda.synchronize()
+        if net is wide:
+            got = (y.clone(), [v.clone() for v in views])
+            if first is None:
+                first = got
+            else:
+                assert torch.equal(y, first[0])
+                for a, b in zip(got[1], first[1]):
+                    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
