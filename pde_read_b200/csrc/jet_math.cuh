@@ -114,9 +114,11 @@ PDR_HD void jet_mul_adj(const T* a, const T* b, const T* cbar, T* abar, T* bbar)
 //     k y_k = sum_{j=1..k} j z_j w_{k-j},   w_k = -sum_{i=0..k} y_i y_{k-i}  (k >= 1)
 // (reference activation: torch.nn.Tanh, Network.py:158-160)
 // ---------------------------------------------------------------------------------------------
+// Everything in the tanh jet depends on z_0 only through y_0 = tanh(z_0): the series part takes y_0 as given (the
+// reverse kernels stash y_0 in the slot of z_0 and never evaluate tanh again).  z[0] is not read.
 template <int NX, int NT, typename T>
-PDR_HD void tanh_fwd(const T* z, T* y, T* w) {
-    y[0] = pdr_tanh(z[0]);
+PDR_HD void tanh_series(T y0, const T* z, T* y, T* w) {
+    y[0] = y0;
     w[0] = T(1) - y[0] * y[0];
 #pragma unroll
     for (int S = 0; S < 2; ++S) {
@@ -144,10 +146,37 @@ PDR_HD void tanh_fwd(const T* z, T* y, T* w) {
 }
 
 template <int NX, int NT, typename T>
-PDR_HD void tanh_vjp(const T* z, const T* ybar_in, T* zbar) {
+PDR_HD void tanh_fwd(const T* z, T* y, T* w) {
+    tanh_series<NX, NT, T>(pdr_tanh(z[0]), z, y, w);
+}
+
+// w = 1 - y^2 as a jet, from a known y jet
+template <int NX, int NT, typename T>
+PDR_HD void tanh_w_from_y(const T* y, T* w) {
+    w[0] = T(1) - y[0] * y[0];
+#pragma unroll
+    for (int S = 0; S < 2; ++S) {
+        const int N = (S == 0) ? NX : NT;
+        const int off = (S == 0) ? 0 : NX;
+#pragma unroll
+        for (int k = 1; k <= N; ++k) {
+            if (k < N) {
+                T s = T(2) * y[0] * y[off + k];
+#pragma unroll
+                for (int i = 1; i < k; ++i) s += y[off + i] * y[off + k - i];
+                w[off + k] = -s;
+            } else {
+                w[off + k] = T(0);   // never read
+            }
+        }
+    }
+}
+
+// adjoint of the series recurrences given the forward jets y, w (z[0] is not read)
+template <int NX, int NT, typename T>
+PDR_HD void tanh_vjp_core(const T* z, const T* y, const T* w, const T* ybar_in, T* zbar) {
     constexpr int J = 1 + NX + NT;
-    T y[J], w[J], yb[J], wb[J];
-    tanh_fwd<NX, NT, T>(z, y, w);
+    T yb[J], wb[J];
 #pragma unroll
     for (int i = 0; i < J; ++i) { yb[i] = ybar_in[i]; wb[i] = T(0); zbar[i] = T(0); }
 #pragma unroll
@@ -178,6 +207,23 @@ PDR_HD void tanh_vjp(const T* z, const T* ybar_in, T* zbar) {
     // w_0 = 1 - y_0^2 ;  y_0 = tanh z_0
     yb[0] += -T(2) * y[0] * wb[0];
     zbar[0] = yb[0] * w[0];
+}
+
+template <int NX, int NT, typename T>
+PDR_HD void tanh_vjp(const T* z, const T* ybar_in, T* zbar) {
+    constexpr int J = 1 + NX + NT;
+    T y[J], w[J];
+    tanh_fwd<NX, NT, T>(z, y, w);
+    tanh_vjp_core<NX, NT, T>(z, y, w, ybar_in, zbar);
+}
+
+// the same with the forward jet y = tanh(z) supplied by the caller (z[0] is not read)
+template <int NX, int NT, typename T>
+PDR_HD void tanh_vjp_y(const T* z, const T* y, const T* ybar_in, T* zbar) {
+    constexpr int J = 1 + NX + NT;
+    T w[J];
+    tanh_w_from_y<NX, NT, T>(y, w);
+    tanh_vjp_core<NX, NT, T>(z, y, w, ybar_in, zbar);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -237,10 +237,11 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
                             float z[J], y[J];
 #pragma unroll
                             for (int j = 0; j < J; ++j) z[j] = acc[q][j][n];
+                            act_fwd<ACT, NX, NT, float>(z, ab, y);
                             if (STASH) {
+                                if (ACT == ACT_TANH) z[0] = y[0];       // see "rows of the reverse pass"
                                 stash_store<J>(a.stash + (((size_t)tile * (L - 1) + (l - 1)) * W + i) * (J * TP) + pt * J, z);
                             }
-                            act_fwd<ACT, NX, NT, float>(z, ab, y);
                             if (last) {
 #pragma unroll
                                 for (int j = 0; j < J; ++j) part[q][j] = fmaf(wo, y[j], part[q][j]);
@@ -382,6 +383,39 @@ __device__ __forceinline__ void wgrad_tiles(const float* __restrict__ ZB, const 
     }
 }
 
+// ---- rows of the reverse pass ------------------------------------------------------------------------------
+// A "row" is the pre-activation jet of one (neuron, point) as the reverse kernel sees it.  For tanh its slot 0
+// holds y_0 = tanh(z_0) instead of z_0 (written so by the forward kernel's stash): every other coefficient of the
+// tanh jet and of its adjoint depends on z_0 only through y_0, so the reverse pass never evaluates tanh, and the
+// VJP takes the forward jet y from shared memory (it is there for the weight gradient) instead of recomputing it.
+template <int ACT>
+struct VJP_FROM_Y {
+    static constexpr bool v = (ACT == ACT_TANH);
+};
+
+template <int ACT, int NX, int NT>
+__device__ __forceinline__ void input_layer_row(const NetDev& net, const float* IN, int TP, int i, int pt, float* z) {
+    input_layer_jet<NX, NT>(net, IN, TP, i, pt, z);
+    if (ACT == ACT_TANH) z[0] = pdr_tanh(z[0]);
+}
+
+template <int ACT, int NX, int NT>
+__device__ __forceinline__ void act_fwd_row(const float* z, const float* ab, float* y) {
+    if (ACT == ACT_TANH) {
+        float w[1 + NX + NT];
+        tanh_series<NX, NT, float>(z[0], z, y, w);
+    } else {
+        act_fwd<ACT, NX, NT, float>(z, ab, y);
+    }
+}
+
+template <int ACT, int NX, int NT>
+__device__ __forceinline__ void act_vjp_row(const float* z, const float* y, const float* ab, const float* ybar,
+                                            float* zbar, float* abbar) {
+    if (ACT == ACT_TANH) tanh_vjp_y<NX, NT, float>(z, y, ybar, zbar);
+    else                 act_vjp<ACT, NX, NT, float>(z, ab, ybar, zbar, abbar);
+}
+
 template <int ACT, int NX, int NT>
 __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_kernel(const BwdArgs a) {
     constexpr int J = 1 + NX + NT;
@@ -394,9 +428,9 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
     const int W = net.W, L = net.L, din = net.din, NC = net.NC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
-    float* ZB = smem;                          // adjoint of pre-activations of the current layer
-    float* HP = ZB + (size_t)W * HS;           // activations of the layer below / adjoint of them
-    float* IN = HP + (size_t)W * HS;           // [din][TP]
+    float* Zb = smem;                          // zbar of the layer above the current weight matrix ...
+    float* Yb = Zb + (size_t)W * HS;           // ... activations of the layer below it (the two swap every layer)
+    float* IN = Yb + (size_t)W * HS;           // [din][TP]
     float* SD = IN + din * TP;                 // [J][TP] seeds = d(loss)/d(u_j), factorials folded in
     float* GIN = SD + J * TP;                  // [din][TP]
     float* SACC = GIN + din * TP;              // small-parameter gradient accumulators (persist over tiles)
@@ -406,8 +440,8 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
     const int sab = swout + W;                 // rational coefficients [L][7]
     const int NS = sab + 7 * L;
 
-    // activation phases: one work item = G neurons; blocks with more warps than neuron chunks (wide networks,
-    // one CTA per SM) hand out single neurons so that all warps take part
+    // activation-only phases: one work item = G neurons; blocks with more warps than neuron chunks (wide
+    // networks, one CTA per SM) hand out single neurons so that all warps take part
     const int G = (nwarps > NC) ? 1 : TN;
     const int nitems = (W + G - 1) / G;
 
@@ -459,148 +493,53 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
             if (lane == 0) SACC[sbL] += s;
         }
 
-        // ---- VJP through hidden layer `lv` (top first).  ybar comes from the output layer
-        //      for the top layer, otherwise from HP (written by the product with W^T below).
-        for (int lv = L - 1; lv >= 0; --lv) {
-            const bool top = (lv == L - 1);
-            if (!top) {
-                const int l = lv + 1;   // weight matrix between hidden layers lv and lv+1
-                // HP holds h^{lv} = act(z^{lv}): written by phase (d) of the iteration above (see there)
-                // (b) weight gradient of matrix l:  gW[i][k] += sum_r ZB[i][r] HP[k][r]
-                {
-                    float* gw = gp + a.lay.off_w[l];
-                    if (a.wg_mode == 1) wgrad_tiles<5, 4>(ZB, HP, W, HS, J * TP, gw);
-                    else                wgrad_tiles<4, 4>(ZB, HP, W, HS, J * TP, gw);
-                }
-                __syncthreads();
-                // (c) HP = hbar^{lv}[k] = sum_i W_l[i][k] ZB[i]
-                const float* wp = a.wn_packed + (size_t)(l - 1) * W * NC * TNP;
-                for (int c = warp; c < NC; c += nwarps) {
-                    float2 acc2[PPL][J][TN / 2];
-#pragma unroll
-                    for (int q = 0; q < PPL; ++q)
-#pragma unroll
-                        for (int j = 0; j < J; ++j)
-#pragma unroll
-                            for (int n = 0; n < TN / 2; ++n) acc2[q][j][n] = make_float2(0.f, 0.f);
-                    const float* wi = wp + c * TNP;
-                    const float* zi = ZB + lane;
-#pragma unroll 2
-                    for (int i = 0; i < W; ++i) {
-                        product_step<PPL, J>(acc2, zi, TP, wi);
-                        wi += NC * TNP;
-                        zi += HS;
-                    }
-                    float acc[PPL][J][TN];
-#pragma unroll
-                    for (int q = 0; q < PPL; ++q)
-#pragma unroll
-                        for (int j = 0; j < J; ++j)
-#pragma unroll
-                            for (int n = 0; n < TN / 2; ++n) {
-                                acc[q][j][2 * n] = acc2[q][j][n].x;
-                                acc[q][j][2 * n + 1] = acc2[q][j][n].y;
-                            }
-#pragma unroll
-                    for (int n = 0; n < TN; ++n) {
-                        const int k = c * TN + n;
-                        if (k < W) {
-#pragma unroll
-                            for (int q = 0; q < PPL; ++q)
-#pragma unroll
-                                for (int j = 0; j < J; ++j) HP[(size_t)k * HS + j * TP + q * 32 + lane] = acc[q][j][n];
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-
-            // (d) VJP of the activation of hidden layer lv:  ZB = zbar^{lv}.  The same pass re-evaluates the
-            //     activations of the layer below, HP = h^{lv-1} = act(z^{lv-1}), which the next iteration's weight
-            //     gradient needs: an independent dependency chain in the same loop (each thread overwrites the
-            //     hbar element it has just read).
+        // ---- top hidden layer: ybar = w_out * seed.  Zb <- zbar^{L-1}, Yb <- y^{L-2} (for the first weight gradient)
+        {
+            const int lv = L - 1;
             float ab[7], ab_lo[7], abbar[7];
             load_ab<ACT>(net, lv, ab);
             load_ab<ACT>(net, lv > 0 ? lv - 1 : 0, ab_lo);
 #pragma unroll
             for (int t = 0; t < 7; ++t) abbar[t] = 0.f;
+            const float* st_z = a.stash + ((size_t)tile * (L - 1) + (lv > 0 ? lv - 1 : 0)) * W * (J * TP);
+            const float* st_zl = a.stash + ((size_t)tile * (L - 1) + (lv > 1 ? lv - 2 : 0)) * W * (J * TP);
             for (int c = warp; c < nitems; c += nwarps) {
+                const int iend = min((c + 1) * G, W);
 #pragma unroll 1
-                for (int n = 0; n < G; ++n) {
-                    const int i = c * G + n;
-                    if (i >= W) break;
-                    const float wo = top ? __ldg(wout + i) : 0.f;
-                    float gb = 0.f, gwo = 0.f, gx = 0.f, gt = 0.f;
-                    float gwin[MAXD];
-#pragma unroll
-                    for (int d = 0; d < MAXD; ++d) gwin[d] = 0.f;
+                for (int i = c * G; i < iend; ++i) {
+                    const float wo = __ldg(wout + i);
+                    float gb = 0.f, gwo = 0.f;
 #pragma unroll
                     for (int q = 0; q < PPL; ++q) {
                         const int pt = q * 32 + lane;
-                        float z[J], ybar[J], zbar[J];
-                        if (lv == 0) {
-                            input_layer_jet<NX, NT>(net, IN, TP, i, pt, z);
-                        } else {
-                            stash_load<J>(a.stash + (((size_t)tile * (L - 1) + (lv - 1)) * W + i) * (J * TP) + pt * J, z);
-                        }
-                        if (top) {
-                            float y[J];
-                            act_fwd<ACT, NX, NT, float>(z, ab, y);
-#pragma unroll
-                            for (int j = 0; j < J; ++j) {
-                                const float sd = SD[j * TP + pt];
-                                ybar[j] = wo * sd;
-                                gwo = fmaf(sd, y[j], gwo);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < J; ++j) ybar[j] = HP[(size_t)i * HS + j * TP + pt];
-                        }
+                        float z[J], y[J], ybar[J], zbar[J];
+                        if (lv == 0) input_layer_row<ACT, NX, NT>(net, IN, TP, i, pt, z);
+                        else         stash_load<J>(st_z + (size_t)i * (J * TP) + pt * J, z);
                         if (lv > 0) {
                             float zl[J], yl[J];
-                            if (lv == 1) {
-                                input_layer_jet<NX, NT>(net, IN, TP, i, pt, zl);
-                            } else {
-                                stash_load<J>(a.stash + (((size_t)tile * (L - 1) + (lv - 2)) * W + i) * (J * TP) + pt * J, zl);
-                            }
-                            act_fwd<ACT, NX, NT, float>(zl, ab_lo, yl);
+                            if (lv == 1) input_layer_row<ACT, NX, NT>(net, IN, TP, i, pt, zl);
+                            else         stash_load<J>(st_zl + (size_t)i * (J * TP) + pt * J, zl);
+                            act_fwd_row<ACT, NX, NT>(zl, ab_lo, yl);
 #pragma unroll
-                            for (int j = 0; j < J; ++j) HP[(size_t)i * HS + j * TP + pt] = yl[j];
+                            for (int j = 0; j < J; ++j) Yb[(size_t)i * HS + j * TP + pt] = yl[j];
                         }
-                        act_vjp<ACT, NX, NT, float>(z, ab, ybar, zbar, abbar);
+                        act_fwd_row<ACT, NX, NT>(z, ab, y);
 #pragma unroll
-                        for (int j = 0; j < J; ++j) ZB[(size_t)i * HS + j * TP + pt] = zbar[j];
+                        for (int j = 0; j < J; ++j) {
+                            const float sd = SD[j * TP + pt];
+                            ybar[j] = wo * sd;
+                            gwo = fmaf(sd, y[j], gwo);
+                        }
+                        act_vjp_row<ACT, NX, NT>(z, y, ab, ybar, zbar, abbar);
+#pragma unroll
+                        for (int j = 0; j < J; ++j) Zb[(size_t)i * HS + j * TP + pt] = zbar[j];
                         gb += zbar[0];
-                        if (lv == 0) {
-                            if (NX > 0) gx += zbar[1];
-                            if (NT > 0) gt += zbar[NX + 1];
-                            const float* wrow = net.w[0] + (size_t)i * din;
-#pragma unroll
-                            for (int d = 0; d < MAXD; ++d) {
-                                if (d < din) {
-                                    gwin[d] = fmaf(zbar[0], IN[d * TP + pt], gwin[d]);
-                                    if (a.gin != nullptr) atomicAdd(&GIN[d * TP + pt], __ldg(wrow + d) * zbar[0]);
-                                }
-                            }
-                        }
                     }
                     gb = warp_sum(gb);
-                    if (top) gwo = warp_sum(gwo);
-                    if (lv == 0) {
-                        if (NX > 0) gwin[1] += gx;
-                        if (NT > 0) gwin[0] += gt;
-#pragma unroll
-                        for (int d = 0; d < MAXD; ++d)
-                            if (d < din) gwin[d] = warp_sum(gwin[d]);
-                    }
+                    gwo = warp_sum(gwo);
                     if (lane == 0) {
                         SACC[lv * W + i] += gb;
-                        if (top) SACC[swout + i] += gwo;
-                        if (lv == 0) {
-#pragma unroll
-                            for (int d = 0; d < MAXD; ++d)
-                                if (d < din) SACC[sw0 + i * din + d] += gwin[d];
-                        }
+                        SACC[swout + i] += gwo;
                     }
                 }
             }
@@ -613,6 +552,151 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
             }
             __syncthreads();
         }
+
+        // ---- hidden layers below, top down.  At the head of a trip Zb = zbar^{lv+1}, Yb = y^{lv}.
+        for (int lv = L - 2; lv >= 0; --lv) {
+            const int l = lv + 1;   // weight matrix between hidden layers lv and lv+1
+            // (b) weight gradient of matrix l:  gW[i][k] += sum_r Zb[i][r] Yb[k][r]
+#ifndef PDR_SKIP_WGRAD
+            {
+                float* gw = gp + a.lay.off_w[l];
+                if (a.wg_mode == 1) wgrad_tiles<5, 4>(Zb, Yb, W, HS, J * TP, gw);
+                else                wgrad_tiles<4, 4>(Zb, Yb, W, HS, J * TP, gw);
+            }
+#endif
+            __syncthreads();
+            // (c) ybar^{lv}[k] = sum_i W_l[i][k] Zb[i] stays in the registers of the thread that owns (k, point), and
+            //     the activation VJP runs in the same thread, unrolled over the TN neurons of the chunk: zbar^{lv}
+            //     replaces y^{lv} in Yb (elements private to the thread), Zb is only read in this phase.
+            float ab[7], abbar[7];
+            load_ab<ACT>(net, lv, ab);
+#pragma unroll
+            for (int t = 0; t < 7; ++t) abbar[t] = 0.f;
+            const float* st_z = a.stash + ((size_t)tile * (L - 1) + (lv > 0 ? lv - 1 : 0)) * W * (J * TP);
+            const float* wp = a.wn_packed + (size_t)(l - 1) * W * NC * TNP;
+            for (int c = warp; c < NC; c += nwarps) {
+                float2 acc2[PPL][J][TN / 2];
+#pragma unroll
+                for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                    for (int j = 0; j < J; ++j)
+#pragma unroll
+                        for (int n = 0; n < TN / 2; ++n) acc2[q][j][n] = make_float2(0.f, 0.f);
+                const float* wi = wp + c * TNP;
+                const float* zi = Zb + lane;
+#pragma unroll 2
+                for (int i = 0; i < W; ++i) {
+                    product_step<PPL, J>(acc2, zi, TP, wi);
+                    wi += NC * TNP;
+                    zi += HS;
+                }
+#pragma unroll
+                for (int n = 0; n < TN; ++n) {
+                    const int k = c * TN + n;
+                    if (k < W) {
+                        float gb = 0.f;
+#pragma unroll
+                        for (int q = 0; q < PPL; ++q) {
+                            const int pt = q * 32 + lane;
+                            float z[J], y[J], ybar[J], zbar[J];
+                            if (lv == 0) input_layer_row<ACT, NX, NT>(net, IN, TP, k, pt, z);
+                            else         stash_load<J>(st_z + (size_t)k * (J * TP) + pt * J, z);
+#pragma unroll
+                            for (int j = 0; j < J; ++j) {
+                                ybar[j] = (n & 1) ? acc2[q][j][n / 2].y : acc2[q][j][n / 2].x;
+                                y[j] = VJP_FROM_Y<ACT>::v ? Yb[(size_t)k * HS + j * TP + pt] : 0.f;
+                            }
+                            act_vjp_row<ACT, NX, NT>(z, y, ab, ybar, zbar, abbar);
+#pragma unroll
+                            for (int j = 0; j < J; ++j) Yb[(size_t)k * HS + j * TP + pt] = zbar[j];
+                            gb += zbar[0];
+                        }
+                        gb = warp_sum(gb);
+                        if (lane == 0) SACC[lv * W + k] += gb;
+                    }
+                }
+            }
+            if (ACT == ACT_RATIONAL) {
+#pragma unroll
+                for (int t = 0; t < 7; ++t) {
+                    const float s = warp_sum(abbar[t]);
+                    if (lane == 0) atomicAdd(&SACC[sab + 7 * lv + t], s);
+                }
+            }
+            __syncthreads();
+            // (d) Zb (dead now) <- y^{lv-1} = act(z^{lv-1}) for the next weight gradient
+            if (lv > 0) {
+                float ab_lo[7];
+                load_ab<ACT>(net, lv - 1, ab_lo);
+                const float* st_zl = a.stash + ((size_t)tile * (L - 1) + (lv > 1 ? lv - 2 : 0)) * W * (J * TP);
+                for (int c = warp; c < nitems; c += nwarps) {
+                    const int iend = min((c + 1) * G, W);
+#pragma unroll 2
+                    for (int i = c * G; i < iend; ++i) {
+#pragma unroll
+                        for (int q = 0; q < PPL; ++q) {
+                            const int pt = q * 32 + lane;
+                            float zl[J], yl[J];
+                            if (lv == 1) input_layer_row<ACT, NX, NT>(net, IN, TP, i, pt, zl);
+                            else         stash_load<J>(st_zl + (size_t)i * (J * TP) + pt * J, zl);
+                            act_fwd_row<ACT, NX, NT>(zl, ab_lo, yl);
+#pragma unroll
+                            for (int j = 0; j < J; ++j) Zb[(size_t)i * HS + j * TP + pt] = yl[j];
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            float* t = Zb; Zb = Yb; Yb = t;
+        }
+
+        // ---- input layer: Zb = zbar^0.  d/dW_0[i][d] = sum_p zbar_0 in_d (+ the series seeds: the x-series enters
+        //      through input column 1, the t-series through column 0), d/d in_d = sum_i W_0[i][d] zbar_0
+        for (int c = warp; c < nitems; c += nwarps) {
+            const int iend = min((c + 1) * G, W);
+            float gi[PPL][MAXD];
+#pragma unroll
+            for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                for (int d = 0; d < MAXD; ++d) gi[q][d] = 0.f;
+#pragma unroll 1
+            for (int i = c * G; i < iend; ++i) {
+                const float* wrow = net.w[0] + (size_t)i * din;
+                float gwin[MAXD];
+#pragma unroll
+                for (int d = 0; d < MAXD; ++d) gwin[d] = 0.f;
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) {
+                    const int pt = q * 32 + lane;
+                    const float zb0 = Zb[(size_t)i * HS + pt];
+                    if (NX > 0) gwin[1] += Zb[(size_t)i * HS + 1 * TP + pt];
+                    if (NT > 0) gwin[0] += Zb[(size_t)i * HS + (NX + 1) * TP + pt];
+#pragma unroll
+                    for (int d = 0; d < MAXD; ++d) {
+                        if (d < din) {
+                            gwin[d] = fmaf(zb0, IN[d * TP + pt], gwin[d]);
+                            gi[q][d] = fmaf(__ldg(wrow + d), zb0, gi[q][d]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < MAXD; ++d)
+                    if (d < din) gwin[d] = warp_sum(gwin[d]);
+                if (lane == 0) {
+#pragma unroll
+                    for (int d = 0; d < MAXD; ++d)
+                        if (d < din) SACC[sw0 + i * din + d] += gwin[d];
+                }
+            }
+            if (a.gin != nullptr) {
+#pragma unroll
+                for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                    for (int d = 0; d < MAXD; ++d)
+                        if (d < din) atomicAdd(&GIN[d * TP + q * 32 + lane], gi[q][d]);
+            }
+        }
+        __syncthreads();
 
         if (a.gin != nullptr) {
             for (int idx = threadIdx.x; idx < din * TP; idx += blockDim.x) {
