@@ -78,7 +78,7 @@ size_t fwd_smem_bytes(int W, int din, int J, int nwarps) {
 }
 size_t bwd_smem_bytes(int W, int L, int din, int J) {
     const int TP = tile_points(J), HS = h_stride(J);
-    const size_t ns = (size_t)L * W + 1 + (size_t)W * din + W + 7 * L;
+    const size_t ns = (((size_t)L * W + 1 + (size_t)W * din + W + 7 * L + 3) & ~(size_t)3) + HS;   // + the ones row
     return sizeof(float) * ((size_t)2 * W * HS + (size_t)2 * din * TP + (size_t)J * TP + ns);
 }
 
@@ -870,11 +870,20 @@ static int plan_backward_launch(int act, int nx, int nt, BwdPlan& p, BwdArgs b, 
     b.wn_packed = p.wn;
     b.num_tiles = (b.M + TP - 1) / TP;
     {
-        // weight-gradient register tiling: 5x4 or 4x4 outputs per thread, whichever needs fewer (rounds x outputs)
-        const int threads = bwd_block_warps(b.net.W, b.net.L, b.net.din, jet_len(nx, nt)) * 32, W = b.net.W;
-        const int t54 = ((W + 4) / 5) * ((W + 3) / 4), t44 = ((W + 3) / 4) * ((W + 3) / 4);
-        const int c54 = ((t54 + threads - 1) / threads) * 20, c44 = ((t44 + threads - 1) / threads) * 16;
-        b.wg_mode = (c54 <= c44) ? 1 : 0;
+        // weight-gradient tiling: a warp owns 10 x (16 TK) outputs, TK in {2, 3, 4}; take the one with the fewest
+        // (rounds x outputs per thread) over W x (W + 1 bias column); ties go to the larger tile (fewer
+        // shared-memory wavefronts per FMA)
+        const int nw = bwd_block_warps(b.net.W, b.net.L, b.net.din, jet_len(nx, nt)), W = b.net.W;
+        long best = -1;
+        for (int m = 2; m >= 0; --m) {
+            const int tk = 2 + m;
+            const int tasks = ((W + 9) / 10) * ((W + 1 + 16 * tk - 1) / (16 * tk));
+            const long cost = (long)((tasks + nw - 1) / nw) * tk;
+            if (best < 0 || cost < best) {
+                best = cost;
+                b.wg_mode = m;
+            }
+        }
     }
     int g = p.grid;
     if (b.num_tiles < g) g = (int)b.num_tiles;

@@ -318,26 +318,40 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
 // =============================================================================================
 
 // weight-gradient micro kernel: gW[i][k] += sum_r ZB[i][r] * HP[k][r],  r over (jet, point).
-// Thread-tile (mi, mk) owns rows i = mi + MI*ti and columns k = mk + MK*tk (strided, so that
-// consecutive lanes read consecutive shared-memory rows: row stride HS = 4 mod 32 words).
+// The phase is bound by shared-memory wavefronts, not FMAs, so the lane -> output mapping is chosen for the
+// cheapest 16-byte loads the hardware offers (measured with tests/lds_probe: a warp-wide LDS.128 costs 2
+// wavefronts when the lanes' addresses form runs of equal addresses over consecutive rows (row stride = 4 mod 32
+// banks) or alternate between two rows, 4 or more for modulo / scattered patterns):
+//   lane = 2 a + b;  rows i = i0 + b + 2 ti (2 rows per load, alternating lanes),
+//                    columns k = k0 + a + 16 tk (16 consecutive rows per load, runs of 2 lanes)
+// so that every load is a 2-wavefront one and a warp owns a (2 TI) x (16 TK) block of the gradient; TI = 5 makes
+// the row block one neuron chunk (TN = 10 rows), so a block of NC warps covers a layer in one round per column block.
+// Column k = W is the bias gradient: its "activation" row is ONES (1 over the order-0 block of the row, 0 over the
+// higher jet coefficients), so gb[i] = sum_p ZB[i][0][p] falls out of the same tiles.
 template <int TI, int TK>
-__device__ __forceinline__ void wgrad_tiles(const float* __restrict__ ZB, const float* __restrict__ HP, int W,
-                                            int HS, int R, float* __restrict__ gw) {
-    const int MI = (W + TI - 1) / TI, MK = (W + TK - 1) / TK;
-    const int ntile = MI * MK;
-    for (int t = threadIdx.x; t < ntile; t += blockDim.x) {
-        const int mi = t / MK, mk = t - mi * MK;
+__device__ __forceinline__ void wgrad_tiles(const float* __restrict__ ZB, const float* __restrict__ HP,
+                                            const float* __restrict__ ONES, int W, int HS, int R,
+                                            float* __restrict__ gw, float* __restrict__ gb) {
+    constexpr int RT = 2 * TI, CT = 16 * TK;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int la = lane >> 1, lb = lane & 1;
+    const int WK = W + 1;   // + the bias column
+    const int nrt = (W + RT - 1) / RT, nct = (WK + CT - 1) / CT;
+    for (int task = warp; task < nrt * nct; task += nwarps) {
+        const int rt = task / nct, ct = task - rt * nct;
+        const int i0 = rt * RT + lb, k0 = ct * CT + la;
         const float4* ap[TI];
         const float4* bp[TK];
 #pragma unroll
         for (int ti = 0; ti < TI; ++ti) {
-            const int i = mi + MI * ti;
-            ap[ti] = reinterpret_cast<const float4*>(ZB + (size_t)(i < W ? i : mi) * HS);
+            const int i = i0 + 2 * ti;
+            ap[ti] = reinterpret_cast<const float4*>(ZB + (size_t)(i < W ? i : W - 1) * HS);
         }
 #pragma unroll
         for (int tk = 0; tk < TK; ++tk) {
-            const int k = mk + MK * tk;
-            bp[tk] = reinterpret_cast<const float4*>(HP + (size_t)(k < W ? k : mk) * HS);
+            const int k = k0 + 16 * tk;
+            bp[tk] = reinterpret_cast<const float4*>(
+                k < W ? HP + (size_t)k * HS : (k == W ? ONES : HP + (size_t)(W - 1) * HS));
         }
         // packed fma.rn.f32x2: each output keeps two partial sums (even / odd reduction index), the operand
         // pairs are the .xy / .zw halves of the 16-byte loads
@@ -347,36 +361,33 @@ __device__ __forceinline__ void wgrad_tiles(const float* __restrict__ ZB, const 
 #pragma unroll
             for (int tk = 0; tk < TK; ++tk) acc2[ti][tk] = make_float2(0.f, 0.f);
         const int R4 = R >> 2;
-#pragma unroll 2
+#pragma unroll 1
         for (int r = 0; r < R4; ++r) {
-            float4 av[TI], bv[TK];
+            float4 av[TI];
 #pragma unroll
             for (int ti = 0; ti < TI; ++ti) av[ti] = ap[ti][r];
 #pragma unroll
-            for (int tk = 0; tk < TK; ++tk) bv[tk] = bp[tk][r];
+            for (int tk = 0; tk < TK; ++tk) {
+                const float4 bv = bp[tk][r];
 #pragma unroll
-            for (int ti = 0; ti < TI; ++ti)
-#pragma unroll
-                for (int tk = 0; tk < TK; ++tk) {
+                for (int ti = 0; ti < TI; ++ti) {
                     float2 s2 = acc2[ti][tk];
-                    s2 = __ffma2_rn(make_float2(av[ti].x, av[ti].y), make_float2(bv[tk].x, bv[tk].y), s2);
-                    s2 = __ffma2_rn(make_float2(av[ti].z, av[ti].w), make_float2(bv[tk].z, bv[tk].w), s2);
+                    s2 = __ffma2_rn(make_float2(av[ti].x, av[ti].y), make_float2(bv.x, bv.y), s2);
+                    s2 = __ffma2_rn(make_float2(av[ti].z, av[ti].w), make_float2(bv.z, bv.w), s2);
                     acc2[ti][tk] = s2;
                 }
+            }
         }
-        float acc[TI][TK];
-#pragma unroll
-        for (int ti = 0; ti < TI; ++ti)
-#pragma unroll
-            for (int tk = 0; tk < TK; ++tk) acc[ti][tk] = acc2[ti][tk].x + acc2[ti][tk].y;
 #pragma unroll
         for (int ti = 0; ti < TI; ++ti) {
-            const int i = mi + MI * ti;
+            const int i = i0 + 2 * ti;
             if (i < W) {
 #pragma unroll
                 for (int tk = 0; tk < TK; ++tk) {
-                    const int k = mk + MK * tk;
-                    if (k < W) atomicAdd(&gw[(size_t)i * W + k], acc[ti][tk]);   // private to this CTA; RED avoids the load round trip
+                    const int k = k0 + 16 * tk;
+                    const float v = acc2[ti][tk].x + acc2[ti][tk].y;
+                    if (k < W) atomicAdd(&gw[(size_t)i * W + k], v);   // private to this CTA; RED avoids the load round trip
+                    else if (k == W) atomicAdd(&gb[i], v);                 // shared-memory accumulator
                 }
             }
         }
@@ -416,7 +427,9 @@ __device__ __forceinline__ void act_vjp_row(const float* z, const float* y, cons
     else                 act_vjp<ACT, NX, NT, float>(z, ab, ybar, zbar, abbar);
 }
 
-template <int ACT, int NX, int NT>
+// FUSED: one warp per neuron chunk (blockDim = 32 NC), the VJP runs in the product epilogue.  !FUSED ("wide"
+// blocks of BWD_WIDE_WARPS > NC warps, one CTA per SM): the VJP runs in phase (d), where all warps take part.
+template <int ACT, int NX, int NT, bool FUSED>
 __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_kernel(const BwdArgs a) {
     constexpr int J = 1 + NX + NT;
     constexpr int PPL = PointsPerLane<J>::v;
@@ -439,16 +452,19 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
     const int swout = sw0 + W * din;           // output weights [W]
     const int sab = swout + W;                 // rational coefficients [L][7]
     const int NS = sab + 7 * L;
+    float* ONES = SACC + ((NS + 3) & ~3);      // [HS] 1 over the order-0 block, 0 elsewhere (bias column of wgrad_tiles)
 
     // activation-only phases: one work item = G neurons; blocks with more warps than neuron chunks (wide
     // networks, one CTA per SM) hand out single neurons so that all warps take part
-    const int G = (nwarps > NC) ? 1 : TN;
+    constexpr bool fused = FUSED;
+    const int G = fused ? TN : 1;
     const int nitems = (W + G - 1) / G;
 
     float* gp = a.gpart + (size_t)blockIdx.x * a.lay.total;
     if (!a.accumulate)
         for (int idx = threadIdx.x; idx < a.lay.total; idx += blockDim.x) gp[idx] = 0.f;
     for (int idx = threadIdx.x; idx < NS; idx += blockDim.x) SACC[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < HS; idx += blockDim.x) ONES[idx] = (idx < TP) ? 1.f : 0.f;
     __syncthreads();
 
     const float* wout = net.w[L];
@@ -508,7 +524,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
 #pragma unroll 1
                 for (int i = c * G; i < iend; ++i) {
                     const float wo = __ldg(wout + i);
-                    float gb = 0.f, gwo = 0.f;
+                    float gwo = 0.f;
 #pragma unroll
                     for (int q = 0; q < PPL; ++q) {
                         const int pt = q * 32 + lane;
@@ -533,14 +549,9 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                         act_vjp_row<ACT, NX, NT>(z, y, ab, ybar, zbar, abbar);
 #pragma unroll
                         for (int j = 0; j < J; ++j) Zb[(size_t)i * HS + j * TP + pt] = zbar[j];
-                        gb += zbar[0];
                     }
-                    gb = warp_sum(gb);
                     gwo = warp_sum(gwo);
-                    if (lane == 0) {
-                        SACC[lv * W + i] += gb;
-                        SACC[swout + i] += gwo;
-                    }
+                    if (lane == 0) SACC[swout + i] += gwo;
                 }
             }
             if (ACT == ACT_RATIONAL) {
@@ -556,18 +567,19 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
         // ---- hidden layers below, top down.  At the head of a trip Zb = zbar^{lv+1}, Yb = y^{lv}.
         for (int lv = L - 2; lv >= 0; --lv) {
             const int l = lv + 1;   // weight matrix between hidden layers lv and lv+1
-            // (b) weight gradient of matrix l:  gW[i][k] += sum_r Zb[i][r] Yb[k][r]
-#ifndef PDR_SKIP_WGRAD
+            // (b) weight gradient of matrix l:  gW[i][k] += sum_r Zb[i][r] Yb[k][r]  (+ bias column)
             {
                 float* gw = gp + a.lay.off_w[l];
-                if (a.wg_mode == 1) wgrad_tiles<5, 4>(Zb, Yb, W, HS, J * TP, gw);
-                else                wgrad_tiles<4, 4>(Zb, Yb, W, HS, J * TP, gw);
+                if (a.wg_mode == 2)      wgrad_tiles<5, 4>(Zb, Yb, ONES, W, HS, J * TP, gw, SACC + l * W);
+                else if (a.wg_mode == 1) wgrad_tiles<5, 3>(Zb, Yb, ONES, W, HS, J * TP, gw, SACC + l * W);
+                else                     wgrad_tiles<5, 2>(Zb, Yb, ONES, W, HS, J * TP, gw, SACC + l * W);
             }
-#endif
             __syncthreads();
-            // (c) ybar^{lv}[k] = sum_i W_l[i][k] Zb[i] stays in the registers of the thread that owns (k, point), and
-            //     the activation VJP runs in the same thread, unrolled over the TN neurons of the chunk: zbar^{lv}
-            //     replaces y^{lv} in Yb (elements private to the thread), Zb is only read in this phase.
+            // (c) ybar^{lv}[k] = sum_i W_l[i][k] Zb[i].  Fused blocks (one warp per neuron chunk): ybar stays in the
+            //     registers of the thread that owns (k, point) and the activation VJP runs in the same thread,
+            //     unrolled over the TN neurons of the chunk; zbar^{lv} replaces y^{lv} in Yb (elements private to the
+            //     thread), Zb is only read.  Wide blocks (more warps than chunks) park ybar in Yb and leave the VJP
+            //     to phase (d), where all warps take part.
             float ab[7], abbar[7];
             load_ab<ACT>(net, lv, ab);
 #pragma unroll
@@ -590,33 +602,43 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                     wi += NC * TNP;
                     zi += HS;
                 }
+                if (fused) {
 #pragma unroll
-                for (int n = 0; n < TN; ++n) {
-                    const int k = c * TN + n;
-                    if (k < W) {
-                        float gb = 0.f;
+                    for (int n = 0; n < TN; ++n) {
+                        const int k = c * TN + n;
+                        if (k < W) {
 #pragma unroll
-                        for (int q = 0; q < PPL; ++q) {
-                            const int pt = q * 32 + lane;
-                            float z[J], y[J], ybar[J], zbar[J];
-                            if (lv == 0) input_layer_row<ACT, NX, NT>(net, IN, TP, k, pt, z);
-                            else         stash_load<J>(st_z + (size_t)k * (J * TP) + pt * J, z);
+                            for (int q = 0; q < PPL; ++q) {
+                                const int pt = q * 32 + lane;
+                                float z[J], y[J], ybar[J], zbar[J];
+                                if (lv == 0) input_layer_row<ACT, NX, NT>(net, IN, TP, k, pt, z);
+                                else         stash_load<J>(st_z + (size_t)k * (J * TP) + pt * J, z);
 #pragma unroll
-                            for (int j = 0; j < J; ++j) {
-                                ybar[j] = (n & 1) ? acc2[q][j][n / 2].y : acc2[q][j][n / 2].x;
-                                y[j] = VJP_FROM_Y<ACT>::v ? Yb[(size_t)k * HS + j * TP + pt] : 0.f;
+                                for (int j = 0; j < J; ++j) {
+                                    ybar[j] = (n & 1) ? acc2[q][j][n / 2].y : acc2[q][j][n / 2].x;
+                                    y[j] = VJP_FROM_Y<ACT>::v ? Yb[(size_t)k * HS + j * TP + pt] : 0.f;
+                                }
+                                act_vjp_row<ACT, NX, NT>(z, y, ab, ybar, zbar, abbar);
+#pragma unroll
+                                for (int j = 0; j < J; ++j) Yb[(size_t)k * HS + j * TP + pt] = zbar[j];
                             }
-                            act_vjp_row<ACT, NX, NT>(z, y, ab, ybar, zbar, abbar);
-#pragma unroll
-                            for (int j = 0; j < J; ++j) Yb[(size_t)k * HS + j * TP + pt] = zbar[j];
-                            gb += zbar[0];
                         }
-                        gb = warp_sum(gb);
-                        if (lane == 0) SACC[lv * W + k] += gb;
+                    }
+                } else {
+#pragma unroll
+                    for (int n = 0; n < TN; ++n) {
+                        const int k = c * TN + n;
+                        if (k < W) {
+#pragma unroll
+                            for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                                for (int j = 0; j < J; ++j)
+                                    Yb[(size_t)k * HS + j * TP + q * 32 + lane] = (n & 1) ? acc2[q][j][n / 2].y : acc2[q][j][n / 2].x;
+                        }
                     }
                 }
             }
-            if (ACT == ACT_RATIONAL) {
+            if (fused && ACT == ACT_RATIONAL) {
 #pragma unroll
                 for (int t = 0; t < 7; ++t) {
                     const float s = warp_sum(abbar[t]);
@@ -624,25 +646,60 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                 }
             }
             __syncthreads();
-            // (d) Zb (dead now) <- y^{lv-1} = act(z^{lv-1}) for the next weight gradient
-            if (lv > 0) {
+            // (d) Zb (dead now) <- y^{lv-1} = act(z^{lv-1}) for the next weight gradient; wide blocks also run the
+            //     VJP here: Yb <- zbar^{lv} from the ybar parked there
+            if (lv > 0 || !fused) {
                 float ab_lo[7];
-                load_ab<ACT>(net, lv - 1, ab_lo);
+                load_ab<ACT>(net, lv > 0 ? lv - 1 : 0, ab_lo);
                 const float* st_zl = a.stash + ((size_t)tile * (L - 1) + (lv > 1 ? lv - 2 : 0)) * W * (J * TP);
-                for (int c = warp; c < nitems; c += nwarps) {
-                    const int iend = min((c + 1) * G, W);
+                if (fused) {
+                    for (int c = warp; c < nitems; c += nwarps) {
+                        const int iend = min((c + 1) * TN, W);
 #pragma unroll 2
-                    for (int i = c * G; i < iend; ++i) {
+                        for (int i = c * TN; i < iend; ++i) {
+#pragma unroll
+                            for (int q = 0; q < PPL; ++q) {
+                                const int pt = q * 32 + lane;
+                                float zl[J], yl[J];
+                                if (lv == 1) input_layer_row<ACT, NX, NT>(net, IN, TP, i, pt, zl);
+                                else         stash_load<J>(st_zl + (size_t)i * (J * TP) + pt * J, zl);
+                                act_fwd_row<ACT, NX, NT>(zl, ab_lo, yl);
+#pragma unroll
+                                for (int j = 0; j < J; ++j) Zb[(size_t)i * HS + j * TP + pt] = yl[j];
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int i = warp; i < W; i += nwarps) {
 #pragma unroll
                         for (int q = 0; q < PPL; ++q) {
                             const int pt = q * 32 + lane;
-                            float zl[J], yl[J];
-                            if (lv == 1) input_layer_row<ACT, NX, NT>(net, IN, TP, i, pt, zl);
-                            else         stash_load<J>(st_zl + (size_t)i * (J * TP) + pt * J, zl);
-                            act_fwd_row<ACT, NX, NT>(zl, ab_lo, yl);
+                            float z[J], y[J], ybar[J], zbar[J];
+                            if (lv == 0) input_layer_row<ACT, NX, NT>(net, IN, TP, i, pt, z);
+                            else         stash_load<J>(st_z + (size_t)i * (J * TP) + pt * J, z);
 #pragma unroll
-                            for (int j = 0; j < J; ++j) Zb[(size_t)i * HS + j * TP + pt] = yl[j];
+                            for (int j = 0; j < J; ++j) ybar[j] = Yb[(size_t)i * HS + j * TP + pt];
+                            if (lv > 0) {
+                                float zl[J], yl[J];
+                                if (lv == 1) input_layer_row<ACT, NX, NT>(net, IN, TP, i, pt, zl);
+                                else         stash_load<J>(st_zl + (size_t)i * (J * TP) + pt * J, zl);
+                                act_fwd_row<ACT, NX, NT>(zl, ab_lo, yl);
+#pragma unroll
+                                for (int j = 0; j < J; ++j) Zb[(size_t)i * HS + j * TP + pt] = yl[j];
+                            }
+                            if (VJP_FROM_Y<ACT>::v) act_fwd_row<ACT, NX, NT>(z, ab, y);
+                            act_vjp_row<ACT, NX, NT>(z, y, ab, ybar, zbar, abbar);
+#pragma unroll
+                            for (int j = 0; j < J; ++j) Yb[(size_t)i * HS + j * TP + pt] = zbar[j];
                         }
+                    }
+                }
+                if (!fused && ACT == ACT_RATIONAL) {
+#pragma unroll
+                    for (int t = 0; t < 7; ++t) {
+                        const float s = warp_sum(abbar[t]);
+                        if (lane == 0) atomicAdd(&SACC[sab + 7 * lv + t], s);
                     }
                 }
                 __syncthreads();
@@ -650,7 +707,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
             float* t = Zb; Zb = Yb; Yb = t;
         }
 
-        // ---- input layer: Zb = zbar^0.  d/dW_0[i][d] = sum_p zbar_0 in_d (+ the series seeds: the x-series enters
+        // ---- input layer: Zb = zbar^0.  d/db_0[i] = sum_p zbar_0, d/dW_0[i][d] = sum_p zbar_0 in_d (+ the series seeds: the x-series enters
         //      through input column 1, the t-series through column 0), d/d in_d = sum_i W_0[i][d] zbar_0
         for (int c = warp; c < nitems; c += nwarps) {
             const int iend = min((c + 1) * G, W);
@@ -662,13 +719,14 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
 #pragma unroll 1
             for (int i = c * G; i < iend; ++i) {
                 const float* wrow = net.w[0] + (size_t)i * din;
-                float gwin[MAXD];
+                float gwin[MAXD], gb0 = 0.f;
 #pragma unroll
                 for (int d = 0; d < MAXD; ++d) gwin[d] = 0.f;
 #pragma unroll
                 for (int q = 0; q < PPL; ++q) {
                     const int pt = q * 32 + lane;
                     const float zb0 = Zb[(size_t)i * HS + pt];
+                    gb0 += zb0;
                     if (NX > 0) gwin[1] += Zb[(size_t)i * HS + 1 * TP + pt];
                     if (NT > 0) gwin[0] += Zb[(size_t)i * HS + (NX + 1) * TP + pt];
 #pragma unroll
@@ -682,7 +740,9 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
 #pragma unroll
                 for (int d = 0; d < MAXD; ++d)
                     if (d < din) gwin[d] = warp_sum(gwin[d]);
+                gb0 = warp_sum(gb0);
                 if (lane == 0) {
+                    SACC[i] += gb0;
 #pragma unroll
                     for (int d = 0; d < MAXD; ++d)
                         if (d < din) SACC[sw0 + i * din + d] += gwin[d];
@@ -790,7 +850,10 @@ int bwd_grid(int W, int L, int din, long long num_tiles, int* grid_out) {
     constexpr int J = 1 + NX + NT;
     const int nw = bwd_block_warps(W, L, din, J);
     const size_t smem = bwd_smem_bytes(W, L, din, J);
-    return grid_for((const void*)mlp_jet_bwd_kernel<ACT, NX, NT>, nw * 32, smem, num_tiles, grid_out);
+    const int NC = (W + TN - 1) / TN;
+    const void* k = (nw <= NC) ? (const void*)mlp_jet_bwd_kernel<ACT, NX, NT, true>
+                               : (const void*)mlp_jet_bwd_kernel<ACT, NX, NT, false>;
+    return grid_for(k, nw * 32, smem, num_tiles, grid_out);
 }
 
 template <int ACT, int NX, int NT>
@@ -799,7 +862,8 @@ int launch_bwd_impl(const BwdArgs& a, int grid, cudaStream_t stream) {
     const int nw = bwd_block_warps(a.net.W, a.net.L, a.net.din, J);
     const size_t smem = bwd_smem_bytes(a.net.W, a.net.L, a.net.din, J);
     // (the dynamic shared-memory attribute was set by bwd_grid -> grid_for for this shape)
-    mlp_jet_bwd_kernel<ACT, NX, NT><<<grid, nw * 32, smem, stream>>>(a);
+    if (nw <= a.net.NC) mlp_jet_bwd_kernel<ACT, NX, NT, true><<<grid, nw * 32, smem, stream>>>(a);
+    else                mlp_jet_bwd_kernel<ACT, NX, NT, false><<<grid, nw * 32, smem, stream>>>(a);
     PDR_CUDA_CHECK(cudaGetLastError());
     return PDEREAD_OK;
 }

@@ -24,6 +24,8 @@ def harness():
     dp = ctypes.POINTER(ctypes.c_double)
     lib.jet_harness.argtypes = [ctypes.c_int] * 4 + [dp] * 5
     lib.jet_harness.restype = ctypes.c_int
+    lib.jet_harness_tanh_row.argtypes = [ctypes.c_int] * 3 + [dp] * 3
+    lib.jet_harness_tanh_row.restype = ctypes.c_int
     return lib
 
 
@@ -86,3 +88,23 @@ def test_jet_forward_and_vjp(harness, kind, nx, nt):
         np.testing.assert_allclose(zb, gz.numpy(), rtol=1e-10, atol=1e-11)
         if kind == 2:
             np.testing.assert_allclose(abb, gab.numpy(), rtol=1e-10, atol=1e-11)
+
+
+@pytest.mark.parametrize("nx,nt", [(0, 0), (1, 1), (2, 1), (3, 1), (4, 1), (2, 2), (4, 2), (5, 3)])
+def test_tanh_row_forms_match_the_plain_ones(harness, nx, nt):
+    """The reverse kernels' tanh forms (y_0 carried in the row, forward jet supplied to the VJP, z_0 never read)
+    give the same numbers as the plain forward / VJP."""
+    rng = np.random.default_rng(77 + 10 * nx + nt)
+    J = 1 + nx + nt
+    for trial in range(4):
+        z = rng.normal(size=J) * 0.8
+        yb = rng.normal(size=J)
+        ab = np.zeros(7)
+        y, y_row, zb, zb_row = np.zeros(J), np.zeros(J), np.zeros(J), np.zeros(J)
+        assert harness.jet_harness(0, nx, nt, 0, _ptr(z), _ptr(ab), _ptr(yb), _ptr(y), _ptr(np.zeros(7))) == 0
+        assert harness.jet_harness_tanh_row(nx, nt, 0, _ptr(z), _ptr(yb), _ptr(y_row)) == 0
+        np.testing.assert_allclose(y_row, y, rtol=1e-14, atol=1e-15)
+        assert harness.jet_harness(0, nx, nt, 1, _ptr(z), _ptr(ab), _ptr(yb), _ptr(zb), _ptr(np.zeros(7))) == 0
+        assert harness.jet_harness_tanh_row(nx, nt, 1, _ptr(z), _ptr(yb), _ptr(zb_row)) == 0
+        assert np.isfinite(zb_row).all()
+        np.testing.assert_allclose(zb_row, zb, rtol=1e-13, atol=1e-14)
