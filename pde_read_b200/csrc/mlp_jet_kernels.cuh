@@ -47,11 +47,33 @@ __device__ __forceinline__ void load_ab(const NetDev& net, int l, float* ab) {
 }
 
 
+// Rows of the shared activation buffers keep the J jet coefficients of a point contiguous ([neuron][point][jet], row
+// stride HS): one 16- / 8-byte access per point where J allows
+template <int J>
+__device__ __forceinline__ void row_load(const float* p, float* z) {
+    if constexpr (J % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < J; j += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(p + j);
+            z[j] = v.x; z[j + 1] = v.y; z[j + 2] = v.z; z[j + 3] = v.w;
+        }
+    } else if constexpr (J % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < J; j += 2) {
+            const float2 v = *reinterpret_cast<const float2*>(p + j);
+            z[j] = v.x; z[j + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) z[j] = p[j];
+    }
+}
+
 // One k-step of a layer product, acc[q][j][n] += h[q][j] * w[n] for the TN weights of this warp's chunk,
 // issued as packed fma.rn.f32x2 (two FMAs per instruction, same rounding as fmaf): the weights arrive as
 // aligned pairs from the 16-byte loads, the activation is duplicated into a pair.
 template <int PPL, int J>
-__device__ __forceinline__ void product_step(float2 (&acc)[PPL][J][TN / 2], const float* __restrict__ hk, int TP,
+__device__ __forceinline__ void product_step(float2 (&acc)[PPL][J][TN / 2], const float* __restrict__ hk,
                                              const float* __restrict__ wk) {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(wk));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(wk) + 1);
@@ -59,18 +81,21 @@ __device__ __forceinline__ void product_step(float2 (&acc)[PPL][J][TN / 2], cons
     const float2 bw[TNP / 2] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
                                 make_float2(b1.z, b1.w), make_float2(b2.x, b2.y), make_float2(b2.z, b2.w)};
 #pragma unroll
-    for (int q = 0; q < PPL; ++q)
+    for (int q = 0; q < PPL; ++q) {
+        float hv[J];
+        row_load<J>(hk + q * 32 * J, hv);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const float av = hk[j * TP + q * 32];
-            const float2 a2 = make_float2(av, av);
+            const float2 a2 = make_float2(hv[j], hv[j]);
 #pragma unroll
             for (int n = 0; n < TN / 2; ++n) acc[q][j][n] = __ffma2_rn(a2, bw[n], acc[q][j][n]);
         }
+    }
 }
 
 // Stash rows keep the J jet coefficients of a point contiguous ([.. neuron][point][jet]) so that one lane moves
 // them with a single 16- / 8-byte access when J is a multiple of 4 / 2 (consecutive lanes -> consecutive addresses).
+// The same helper stores rows of the shared activation buffers.
 template <int J>
 __device__ __forceinline__ void stash_store(float* p, const float* z) {
     if constexpr (J % 4 == 0) {
@@ -181,8 +206,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
 #pragma unroll
                         for (int j = 0; j < J; ++j) part[q][j] = fmaf(wo, y[j], part[q][j]);
                     } else {
-#pragma unroll
-                        for (int j = 0; j < J; ++j) Hin[(size_t)i * HS + j * TP + pt] = y[j];
+                        stash_store<J>(Hin + (size_t)i * HS + pt * J, y);
                     }
                 }
             }
@@ -209,10 +233,10 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
                     }
                 }
                 const float* wk = wp + c * TNP;
-                const float* hk = Hin + lane;
+                const float* hk = Hin + lane * J;
 #pragma unroll 2
                 for (int k = 0; k < W; ++k) {
-                    product_step<PPL, J>(acc2, hk, TP, wk);
+                    product_step<PPL, J>(acc2, hk, wk);
                     wk += NC * TNP;
                     hk += HS;
                 }
@@ -246,8 +270,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
 #pragma unroll
                                 for (int j = 0; j < J; ++j) part[q][j] = fmaf(wo, y[j], part[q][j]);
                             } else {
-#pragma unroll
-                                for (int j = 0; j < J; ++j) Hout[(size_t)i * HS + j * TP + pt] = y[j];
+                                stash_store<J>(Hout + (size_t)i * HS + pt * J, y);
                             }
                         }
                     }
@@ -452,7 +475,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
     const int swout = sw0 + W * din;           // output weights [W]
     const int sab = swout + W;                 // rational coefficients [L][7]
     const int NS = sab + 7 * L;
-    float* ONES = SACC + ((NS + 3) & ~3);      // [HS] 1 over the order-0 block, 0 elsewhere (bias column of wgrad_tiles)
+    float* ONES = SACC + ((NS + 3) & ~3);      // [HS] 1 at the order-0 coefficient of every point, 0 elsewhere (bias column)
 
     // activation-only phases: one work item = G neurons; blocks with more warps than neuron chunks (wide
     // networks, one CTA per SM) hand out single neurons so that all warps take part
@@ -464,7 +487,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
     if (!a.accumulate)
         for (int idx = threadIdx.x; idx < a.lay.total; idx += blockDim.x) gp[idx] = 0.f;
     for (int idx = threadIdx.x; idx < NS; idx += blockDim.x) SACC[idx] = 0.f;
-    for (int idx = threadIdx.x; idx < HS; idx += blockDim.x) ONES[idx] = (idx < TP) ? 1.f : 0.f;
+    for (int idx = threadIdx.x; idx < HS; idx += blockDim.x) ONES[idx] = (idx < J * TP && idx % J == 0) ? 1.f : 0.f;
     __syncthreads();
 
     const float* wout = net.w[L];
@@ -536,8 +559,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                             if (lv == 1) input_layer_row<ACT, NX, NT>(net, IN, TP, i, pt, zl);
                             else         stash_load<J>(st_zl + (size_t)i * (J * TP) + pt * J, zl);
                             act_fwd_row<ACT, NX, NT>(zl, ab_lo, yl);
-#pragma unroll
-                            for (int j = 0; j < J; ++j) Yb[(size_t)i * HS + j * TP + pt] = yl[j];
+                            stash_store<J>(Yb + (size_t)i * HS + pt * J, yl);
                         }
                         act_fwd_row<ACT, NX, NT>(z, ab, y);
 #pragma unroll
@@ -547,8 +569,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                             gwo = fmaf(sd, y[j], gwo);
                         }
                         act_vjp_row<ACT, NX, NT>(z, y, ab, ybar, zbar, abbar);
-#pragma unroll
-                        for (int j = 0; j < J; ++j) Zb[(size_t)i * HS + j * TP + pt] = zbar[j];
+                        stash_store<J>(Zb + (size_t)i * HS + pt * J, zbar);
                     }
                     gwo = warp_sum(gwo);
                     if (lane == 0) SACC[swout + i] += gwo;
@@ -595,10 +616,10 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
 #pragma unroll
                         for (int n = 0; n < TN / 2; ++n) acc2[q][j][n] = make_float2(0.f, 0.f);
                 const float* wi = wp + c * TNP;
-                const float* zi = Zb + lane;
+                const float* zi = Zb + lane * J;
 #pragma unroll 2
                 for (int i = 0; i < W; ++i) {
-                    product_step<PPL, J>(acc2, zi, TP, wi);
+                    product_step<PPL, J>(acc2, zi, wi);
                     wi += NC * TNP;
                     zi += HS;
                 }
@@ -616,11 +637,11 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
 #pragma unroll
                                 for (int j = 0; j < J; ++j) {
                                     ybar[j] = (n & 1) ? acc2[q][j][n / 2].y : acc2[q][j][n / 2].x;
-                                    y[j] = VJP_FROM_Y<ACT>::v ? Yb[(size_t)k * HS + j * TP + pt] : 0.f;
+                                    y[j] = 0.f;
                                 }
+                                if (VJP_FROM_Y<ACT>::v) row_load<J>(Yb + (size_t)k * HS + pt * J, y);
                                 act_vjp_row<ACT, NX, NT>(z, y, ab, ybar, zbar, abbar);
-#pragma unroll
-                                for (int j = 0; j < J; ++j) Yb[(size_t)k * HS + j * TP + pt] = zbar[j];
+                                stash_store<J>(Yb + (size_t)k * HS + pt * J, zbar);
                             }
                         }
                     }
@@ -630,10 +651,12 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                         const int k = c * TN + n;
                         if (k < W) {
 #pragma unroll
-                            for (int q = 0; q < PPL; ++q)
+                            for (int q = 0; q < PPL; ++q) {
+                                float ybar[J];
 #pragma unroll
-                                for (int j = 0; j < J; ++j)
-                                    Yb[(size_t)k * HS + j * TP + q * 32 + lane] = (n & 1) ? acc2[q][j][n / 2].y : acc2[q][j][n / 2].x;
+                                for (int j = 0; j < J; ++j) ybar[j] = (n & 1) ? acc2[q][j][n / 2].y : acc2[q][j][n / 2].x;
+                                stash_store<J>(Yb + (size_t)k * HS + (q * 32 + lane) * J, ybar);
+                            }
                         }
                     }
                 }
@@ -664,8 +687,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                                 if (lv == 1) input_layer_row<ACT, NX, NT>(net, IN, TP, i, pt, zl);
                                 else         stash_load<J>(st_zl + (size_t)i * (J * TP) + pt * J, zl);
                                 act_fwd_row<ACT, NX, NT>(zl, ab_lo, yl);
-#pragma unroll
-                                for (int j = 0; j < J; ++j) Zb[(size_t)i * HS + j * TP + pt] = yl[j];
+                                stash_store<J>(Zb + (size_t)i * HS + pt * J, yl);
                             }
                         }
                     }
@@ -678,20 +700,17 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                             float z[J], y[J], ybar[J], zbar[J];
                             if (lv == 0) input_layer_row<ACT, NX, NT>(net, IN, TP, i, pt, z);
                             else         stash_load<J>(st_z + (size_t)i * (J * TP) + pt * J, z);
-#pragma unroll
-                            for (int j = 0; j < J; ++j) ybar[j] = Yb[(size_t)i * HS + j * TP + pt];
+                            row_load<J>(Yb + (size_t)i * HS + pt * J, ybar);
                             if (lv > 0) {
                                 float zl[J], yl[J];
                                 if (lv == 1) input_layer_row<ACT, NX, NT>(net, IN, TP, i, pt, zl);
                                 else         stash_load<J>(st_zl + (size_t)i * (J * TP) + pt * J, zl);
                                 act_fwd_row<ACT, NX, NT>(zl, ab_lo, yl);
-#pragma unroll
-                                for (int j = 0; j < J; ++j) Zb[(size_t)i * HS + j * TP + pt] = yl[j];
+                                stash_store<J>(Zb + (size_t)i * HS + pt * J, yl);
                             }
                             if (VJP_FROM_Y<ACT>::v) act_fwd_row<ACT, NX, NT>(z, ab, y);
                             act_vjp_row<ACT, NX, NT>(z, y, ab, ybar, zbar, abbar);
-#pragma unroll
-                            for (int j = 0; j < J; ++j) Yb[(size_t)i * HS + j * TP + pt] = zbar[j];
+                            stash_store<J>(Yb + (size_t)i * HS + pt * J, zbar);
                         }
                     }
                 }
@@ -725,10 +744,10 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
 #pragma unroll
                 for (int q = 0; q < PPL; ++q) {
                     const int pt = q * 32 + lane;
-                    const float zb0 = Zb[(size_t)i * HS + pt];
+                    const float zb0 = Zb[(size_t)i * HS + pt * J];
                     gb0 += zb0;
-                    if (NX > 0) gwin[1] += Zb[(size_t)i * HS + 1 * TP + pt];
-                    if (NT > 0) gwin[0] += Zb[(size_t)i * HS + (NX + 1) * TP + pt];
+                    if (NX > 0) gwin[1] += Zb[(size_t)i * HS + pt * J + 1];
+                    if (NT > 0) gwin[0] += Zb[(size_t)i * HS + pt * J + NX + 1];
 #pragma unroll
                     for (int d = 0; d < MAXD; ++d) {
                         if (d < din) {
