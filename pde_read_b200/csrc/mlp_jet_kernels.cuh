@@ -11,11 +11,15 @@
 // Thread mapping ("lane = point"): a CTA owns a tile of TP = 32*PPL points; lane l of every warp
 // owns points l, l+32, ..; warp w owns chunks of TN output neurons.  In the layer product
 //   z_j[i] = sum_k W[i][k] h_j[k]      (j = jet index, i = output neuron)
-// a thread keeps PPL*J*TN accumulators in registers, reads h_j[k] of its own points from shared
-// memory (conflict-free: consecutive lanes -> consecutive words) and the TN weights W[i0..][k]
-// through the read-only path (same address in all lanes -> one broadcast transaction).  The
+// a thread keeps PPL*J*TN accumulators in registers, reads the jet h[k] of its own points from shared
+// memory (rows [neuron][point][jet]: one vector access per point, conflict-free) and the TN weights
+// W[i0..][k] through the read-only path (same address in all lanes -> one broadcast transaction).  The
 // activation jets are then applied to the accumulators in registers; activations never go to HBM
 // except for the pre-activation stash the reverse pass needs.
+//
+// Reverse pass, per layer (two shared buffers Zb / Yb that swap roles): weight + bias gradients as a
+// register-tiled product of the two buffers; ybar = W^T zbar with the forward mapping and the activation
+// VJP in its epilogue (ybar never leaves the registers); activations of the layer below from the stash.
 #pragma once
 #include <cuda_runtime.h>
 

@@ -472,3 +472,31 @@ def test_one_kernel_alternating_between_network_shapes():
                 assert torch.equal(y, first[0])
                 for a, b in zip(got[1], first[1]):
                     assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("act,LU,WU,LN,WN,m,n", [
+    ("Tanh", 1, 7, 1, 5, 1, 1),          # single hidden layer: no hidden-hidden matrix at all
+    ("Tanh", 2, 11, 2, 9, 1, 2),         # one matrix, one partial neuron chunk
+    ("Rational", 3, 33, 2, 17, 1, 2),    # width = 16 k + 1: one live column in the last weight-gradient block
+    ("Sin", 4, 31, 3, 47, 2, 1),         # 16 k - 1 and a second column block
+    ("Tanh", 3, 65, 2, 96, 1, 3),        # third column block; 7 chunks
+    ("Rational", 2, 128, 2, 40, 1, 4),   # J = 6 at width 128: wide blocks (VJP outside the product epilogue)
+    ("Tanh", 2, 160, 2, 10, 1, 3),       # J = 5 at width 160: wide blocks with as many chunks as warps
+])
+def test_gradients_over_odd_shapes(act, LU, WU, LN, WN, m, n):
+    """Loss and every parameter gradient against the float64 oracle for shapes that exercise the edges of the
+    reverse kernel's tilings (partial chunks, partial weight-gradient blocks, the bias column, depth 1 and 2,
+    wide blocks)."""
+    from pde_read_b200.Loss_Functions import Collocation_Loss
+    su = orc.init_network(LU, WU, 2, act, seed=1000 + WU)
+    sn = orc.init_network(LN, WN, n + 1, act, seed=2000 + WN)
+    U, N = make_net(su, act, 2), make_net(sn, act, n + 1)
+    P = torch.rand(333, 2, generator=torch.Generator().manual_seed(WU)) * 2 - 1
+    loss = Collocation_Loss(U, N, m, n, P.to(DEV), torch.float32, DEV)
+    loss.backward()
+    l32, gs32, gp32 = orc.collocation_loss_and_grads(su, act, sn, act, m, n, P, chunk=1000)
+    l64, gs64, gp64 = orc.collocation_loss_and_grads(to64(su), act, to64(sn), act, m, n, P.double(), chunk=1000)
+    assert abs(loss.item() - l64) <= max(TOL_LOSS * abs(l64), 1.5 * abs(l32 - l64))
+    for pref, net, g32, g64 in (("u.", U, gs32, gs64), ("n.", N, gp32, gp64)):
+        for k, g in grads_of(net).items():
+            assert_close_to_reference(g, g32[k].numpy(), g64[k].numpy(), TOL_GRAD, pref + k)
