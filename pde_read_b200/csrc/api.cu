@@ -72,10 +72,11 @@ int bwd_block_warps(int W, int L, int din, int J) {
     const int nw = block_warps(W);
     return (bwd_smem_bytes(W, L, din, J) > 112 * 1024 && nw < BWD_WIDE_WARPS) ? BWD_WIDE_WARPS : nw;
 }
-size_t fwd_smem_bytes(int W, int din, int J, int nwarps) {
-    const int TP = tile_points(J), HS = h_stride(J);
+size_t fwd_smem_bytes_tile(int W, int din, int J, int nwarps, int TP) {
+    const int HS = J * TP + 4;
     return sizeof(float) * ((size_t)2 * W * HS + (size_t)din * TP + (size_t)nwarps * J * TP);
 }
+size_t fwd_smem_bytes(int W, int din, int J, int nwarps) { return fwd_smem_bytes_tile(W, din, J, nwarps, tile_points(J)); }
 size_t bwd_smem_bytes(int W, int L, int din, int J) {
     const int TP = tile_points(J), HS = h_stride(J);
     const size_t ns = (((size_t)L * W + 1 + (size_t)W * din + W + 7 * L + 3) & ~(size_t)3) + HS;   // + the ones row

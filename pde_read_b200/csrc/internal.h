@@ -23,6 +23,9 @@ constexpr int BWD_WIDE_WARPS = 16;   // warps of the reverse kernel when only on
 #ifndef PDR_PPL_J4
 #define PDR_PPL_J4 1
 #endif
+// points per lane of forward-only (no stash) launches of the plain MLP, J = 1
+constexpr int FWD_ONLY_PPL_J1 = 4;
+
 template <int J>
 struct PointsPerLane {
     static constexpr int v = (J == 1) ? PDR_PPL_J1 : ((J <= 4) ? PDR_PPL_J4 : 1);
@@ -197,6 +200,7 @@ inline int points_per_lane(int J) { return (J == 1) ? PDR_PPL_J1 : ((J <= 4) ? P
 inline int tile_points(int J) { return 32 * points_per_lane(J); }
 inline int h_stride(int J) { return J * tile_points(J) + 4; }
 size_t fwd_smem_bytes(int W, int din, int J, int nwarps);
+size_t fwd_smem_bytes_tile(int W, int din, int J, int nwarps, int TP);   // for an explicit tile of TP points
 size_t bwd_smem_bytes(int W, int L, int din, int J);
 int block_warps(int W);
 int bwd_block_warps(int W, int L, int din, int J);

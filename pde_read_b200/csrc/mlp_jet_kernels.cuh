@@ -153,10 +153,11 @@ __device__ __forceinline__ void input_layer_jet(const NetDev& net, const float* 
 // =============================================================================================
 // forward
 // =============================================================================================
-template <int ACT, int NX, int NT, bool STASH>
+// PPL = points per lane: PointsPerLane<J> (the tile the reverse kernel and the stash use), or FWD_ONLY_PPL_J1 for
+// forward-only calls of the plain MLP (J = 1), whose 3 weight loads per k-step then feed 20 FFMA2 instead of 10.
+template <int ACT, int NX, int NT, bool STASH, int PPL>
 __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_kernel(const FwdArgs a) {
     constexpr int J = 1 + NX + NT;
-    constexpr int PPL = PointsPerLane<J>::v;
     constexpr int TP = 32 * PPL;
     constexpr int HS = J * TP + 4;
 
@@ -850,20 +851,32 @@ inline int grid_for(const void* kernel, int threads, size_t smem, long long num_
     return PDEREAD_OK;
 }
 
-template <int ACT, int NX, int NT>
-int launch_fwd(const FwdArgs& a, cudaStream_t stream) {
+template <int ACT, int NX, int NT, bool STASH, int PPL>
+int launch_fwd_tile(FwdArgs a, cudaStream_t stream) {
     constexpr int J = 1 + NX + NT;
     const int nw = block_warps(a.net.W);
-    const size_t smem = fwd_smem_bytes(a.net.W, a.net.din, J, nw);
-    const void* k = a.stash ? (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, true>
-                            : (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, false>;
+    const size_t smem = fwd_smem_bytes_tile(a.net.W, a.net.din, J, nw, 32 * PPL);
+    a.num_tiles = (a.M + 32 * PPL - 1) / (32 * PPL);
+    const void* k = (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL>;
     int grid = 0;
     int rc = grid_for(k, nw * 32, smem, a.num_tiles, &grid);
     if (rc != PDEREAD_OK) return rc;
-    if (a.stash) mlp_jet_fwd_kernel<ACT, NX, NT, true><<<grid, nw * 32, smem, stream>>>(a);
-    else         mlp_jet_fwd_kernel<ACT, NX, NT, false><<<grid, nw * 32, smem, stream>>>(a);
+    mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL><<<grid, nw * 32, smem, stream>>>(a);
     PDR_CUDA_CHECK(cudaGetLastError());
     return PDEREAD_OK;
+}
+
+template <int ACT, int NX, int NT>
+int launch_fwd(const FwdArgs& a, cudaStream_t stream) {
+    constexpr int J = 1 + NX + NT;
+    constexpr int PPL = PointsPerLane<J>::v;
+    if (a.stash) return launch_fwd_tile<ACT, NX, NT, true, PPL>(a, stream);
+    if constexpr (J == 1 && FWD_ONLY_PPL_J1 != PPL) {
+        // the larger tile only while two CTAs of it still fit an SM
+        if (fwd_smem_bytes_tile(a.net.W, a.net.din, J, block_warps(a.net.W), 32 * FWD_ONLY_PPL_J1) <= 112 * 1024)
+            return launch_fwd_tile<ACT, NX, NT, false, FWD_ONLY_PPL_J1>(a, stream);
+    }
+    return launch_fwd_tile<ACT, NX, NT, false, PPL>(a, stream);
 }
 
 // The backward launch needs the grid size before the call (gpart is sized by it), so the
