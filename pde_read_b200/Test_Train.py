@@ -27,7 +27,7 @@ def Discovery_Training(
     """One epoch: a single Optimizer.step over loss = Collocation_Loss + Data_Loss."""
     Sol_NN.train()
     PDE_NN.train()
-    fast = _fast_closure_ok(Sol_NN, PDE_NN, Collocation_Coords, Data_Coords, Data_Type)
+    fast = _fast_closure_ok(Sol_NN, PDE_NN, Collocation_Coords, Data_Coords, Data_Values, Data_Type)
 
     def Discovery_Closure():
         if torch.is_grad_enabled():
@@ -54,13 +54,18 @@ def Discovery_Training(
 _FAST_CLOSURE = os.environ.get("PDEREAD_FAST_CLOSURE", "1") not in ("0", "", "off")
 
 
-def _fast_closure_ok(Sol_NN, PDE_NN, Collocation_Coords, Data_Coords, Data_Type) -> bool:
+def _fast_closure_ok(Sol_NN, PDE_NN, Collocation_Coords, Data_Coords, Data_Values, Data_Type) -> bool:
     from . import Loss_Functions
     if not _FAST_CLOSURE or Loss_Functions._reducer is not None or Data_Type != torch.float32:
         return False
     if getattr(Sol_NN, "Batch_Norm", False) or getattr(PDE_NN, "Batch_Norm", False):
         return False
-    if not (Collocation_Coords.is_cuda and Data_Coords.is_cuda) or Collocation_Coords.shape[0] == 0 or Data_Coords.shape[0] == 0:
+    if not (Collocation_Coords.is_cuda and Data_Coords.is_cuda) or Collocation_Coords.shape[0] == 0 or Data_Coords.shape[0] < 2:
+        return False
+    # targets as the reference's loader delivers them: one value per data point (anything else takes the reference's
+    # own broadcasting semantics through the autograd path)
+    if not (Data_Values.is_cuda and Data_Values.dim() == 1 and Data_Values.shape[0] == Data_Coords.shape[0]
+            and Data_Values.dtype in (torch.float32, torch.float64)):
         return False
     return all(p.requires_grad for p in list(Sol_NN.parameters()) + list(PDE_NN.parameters()))
 

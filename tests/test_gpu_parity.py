@@ -430,6 +430,14 @@ def test_fused_training_closure_matches_autograd_closure():
     Xd = (torch.rand(700, 2, generator=gen) * 2 - 1).to(DEV)
     yd = torch.sin(Xd[:, 1].double()) * torch.exp(-Xd[:, 0].double())        # float64 targets, as in the shipped npz
     old = Test_Train._FAST_CLOSURE
+    calls = {"fused": 0}
+    inner = Test_Train._fused_closure
+
+    def counting(*a, **k):
+        calls["fused"] += 1
+        return inner(*a, **k)
+
+    Test_Train._fused_closure = counting
     try:
         for opt_name in ("Adam", "LBFGS"):
             results = []
@@ -446,8 +454,10 @@ def test_fused_training_closure_matches_autograd_closure():
                 assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < (2e-5 if opt_name == "Adam" else 2e-3)
             for a, b in zip(results[0][1], results[1][1]):
                 assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < (1e-4 if opt_name == "Adam" else 5e-2)
+        assert calls["fused"] >= 6          # the graph-free path really ran (3 Adam steps + LBFGS re-entries)
     finally:
         Test_Train._FAST_CLOSURE = old
+        Test_Train._fused_closure = inner
 
 
 def test_one_kernel_alternating_between_network_shapes():
