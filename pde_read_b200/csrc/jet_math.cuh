@@ -340,15 +340,12 @@ PDR_HD void rational_fwd(const T* z, const T* ab, T* y) {
     jet_div<NX, NT, T>(P, Q, pdr_rcp(Q[0]), y);
 }
 
+// Adjoint of y = P(z)/Q(z) given the forward quantities s2 = z^2, s3 = z^3, Q, r = 1/Q_0 and y.
 // abbar (7 entries) is accumulated into.
 template <int NX, int NT, typename T>
-PDR_HD void rational_vjp(const T* z, const T* ab, const T* ybar, T* zbar, T* abbar) {
+PDR_HD void rational_vjp_core(const T* z, const T* s2, const T* s3, const T* Q, T r, const T* y, const T* ab,
+                              const T* ybar, T* zbar, T* abbar) {
     constexpr int J = 1 + NX + NT;
-    T s2[J], s3[J], P[J], Q[J], y[J];
-    rational_parts<NX, NT, T>(z, ab, s2, s3, P, Q);
-    const T r = pdr_rcp(Q[0]);
-    jet_div<NX, NT, T>(P, Q, r, y);
-
     // adjoint of the series division: solve the transposed Toeplitz system for Pbar,
     // then Qbar = -(y correlated with Pbar)
     T Pb[J], Qb[J];
@@ -402,6 +399,29 @@ PDR_HD void rational_vjp(const T* z, const T* ab, const T* ybar, T* zbar, T* abb
 
     jet_mul_adj<NX, NT, T>(s2, z, s3b, s2b, zbar);   // s3 = s2 * z
     jet_mul_adj<NX, NT, T>(z, z, s2b, zbar, zbar);   // s2 = z * z
+}
+
+template <int NX, int NT, typename T>
+PDR_HD void rational_vjp(const T* z, const T* ab, const T* ybar, T* zbar, T* abbar) {
+    constexpr int J = 1 + NX + NT;
+    T s2[J], s3[J], P[J], Q[J], y[J];
+    rational_parts<NX, NT, T>(z, ab, s2, s3, P, Q);
+    const T r = pdr_rcp(Q[0]);
+    jet_div<NX, NT, T>(P, Q, r, y);
+    rational_vjp_core<NX, NT, T>(z, s2, s3, Q, r, y, ab, ybar, zbar, abbar);
+}
+
+// the same with the forward jet y = P/Q supplied by the caller: the numerator and the series division are skipped
+template <int NX, int NT, typename T>
+PDR_HD void rational_vjp_y(const T* z, const T* y, const T* ab, const T* ybar, T* zbar, T* abbar) {
+    constexpr int J = 1 + NX + NT;
+    T s2[J], s3[J], Q[J];
+    jet_mul<NX, NT, T>(z, z, s2);
+    jet_mul<NX, NT, T>(s2, z, s3);
+#pragma unroll
+    for (int i = 0; i < J; ++i) Q[i] = ab[5] * z[i] + ab[6] * s2[i];
+    Q[0] += ab[4];
+    rational_vjp_core<NX, NT, T>(z, s2, s3, Q, pdr_rcp(Q[0]), y, ab, ybar, zbar, abbar);
 }
 
 // ---------------------------------------------------------------------------------------------

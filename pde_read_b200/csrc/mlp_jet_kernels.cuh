@@ -473,9 +473,10 @@ __device__ __forceinline__ void wgrad_tiles(const float* __restrict__ ZB, const 
 // holds y_0 = tanh(z_0) instead of z_0 (written so by the forward kernel's stash): every other coefficient of the
 // tanh jet and of its adjoint depends on z_0 only through y_0, so the reverse pass never evaluates tanh, and the
 // VJP takes the forward jet y from shared memory (it is there for the weight gradient) instead of recomputing it.
+// The rational VJP reuses y the same way (its numerator and series division are skipped; z itself stays in the row).
 template <int ACT>
 struct VJP_FROM_Y {
-    static constexpr bool v = (ACT == ACT_TANH);
+    static constexpr bool v = (ACT == ACT_TANH || ACT == ACT_RATIONAL);
 };
 
 template <int ACT, int NX, int NT>
@@ -497,8 +498,9 @@ __device__ __forceinline__ void act_fwd_row(const float* z, const float* ab, flo
 template <int ACT, int NX, int NT>
 __device__ __forceinline__ void act_vjp_row(const float* z, const float* y, const float* ab, const float* ybar,
                                             float* zbar, float* abbar) {
-    if (ACT == ACT_TANH) tanh_vjp_y<NX, NT, float>(z, y, ybar, zbar);
-    else                 act_vjp<ACT, NX, NT, float>(z, ab, ybar, zbar, abbar);
+    if (ACT == ACT_TANH)          tanh_vjp_y<NX, NT, float>(z, y, ybar, zbar);
+    else if (ACT == ACT_RATIONAL) rational_vjp_y<NX, NT, float>(z, y, ab, ybar, zbar, abbar);
+    else                          act_vjp<ACT, NX, NT, float>(z, ab, ybar, zbar, abbar);
 }
 
 // FUSED: one warp per neuron chunk (blockDim = 32 NC), the VJP runs in the product epilogue.  !FUSED ("wide"

@@ -33,6 +33,34 @@ static void run_row_vjp(const double* z, const double* yb, double* zb) {
     tanh_vjp_y<NX, NT, double>(row, y, yb, zb);
 }
 
+template <int NX, int NT>
+static void run_rat_vjp_y(const double* z, const double* ab, const double* yb, double* zb, double* abb) {
+    constexpr int J = 1 + NX + NT;
+    double y[J];
+    rational_fwd<NX, NT, double>(z, ab, y);
+    rational_vjp_y<NX, NT, double>(z, y, ab, yb, zb, abb);
+}
+#define RAT_NT(NX)                                                             \
+    switch (nt) {                                                               \
+        case 0: run_rat_vjp_y<NX, 0>(z, ab, yb, out, abb); return 0;            \
+        case 1: run_rat_vjp_y<NX, 1>(z, ab, yb, out, abb); return 0;            \
+        case 2: run_rat_vjp_y<NX, 2>(z, ab, yb, out, abb); return 0;            \
+        case 3: run_rat_vjp_y<NX, 3>(z, ab, yb, out, abb); return 0;            \
+        default: return -1;                                                     \
+    }
+extern "C" int jet_harness_rational_vjp_y(int nx, int nt, const double* z, const double* ab, const double* yb,
+                                          double* out, double* abb) {
+    switch (nx) {
+        case 0: RAT_NT(0)
+        case 1: RAT_NT(1)
+        case 2: RAT_NT(2)
+        case 3: RAT_NT(3)
+        case 4: RAT_NT(4)
+        case 5: RAT_NT(5)
+        default: return -1;
+    }
+}
+
 #define ROW_NT(NX)                                                                          \
     switch (nt) {                                                                            \
         case 0: if (vjp) run_row_vjp<NX, 0>(z, yb, out); else run_row_fwd<NX, 0>(z, out); return 0; \

@@ -26,6 +26,8 @@ def harness():
     lib.jet_harness.restype = ctypes.c_int
     lib.jet_harness_tanh_row.argtypes = [ctypes.c_int] * 3 + [dp] * 3
     lib.jet_harness_tanh_row.restype = ctypes.c_int
+    lib.jet_harness_rational_vjp_y.argtypes = [ctypes.c_int] * 2 + [dp] * 5
+    lib.jet_harness_rational_vjp_y.restype = ctypes.c_int
     return lib
 
 
@@ -108,3 +110,19 @@ def test_tanh_row_forms_match_the_plain_ones(harness, nx, nt):
         assert harness.jet_harness_tanh_row(nx, nt, 1, _ptr(z), _ptr(yb), _ptr(zb_row)) == 0
         assert np.isfinite(zb_row).all()
         np.testing.assert_allclose(zb_row, zb, rtol=1e-13, atol=1e-14)
+
+
+@pytest.mark.parametrize("nx,nt", [(0, 0), (1, 1), (2, 1), (3, 1), (4, 1), (2, 2), (4, 2), (5, 3)])
+def test_rational_vjp_with_supplied_forward_jet(harness, nx, nt):
+    """rational_vjp_y (forward jet y supplied, numerator and series division skipped) == rational_vjp."""
+    rng = np.random.default_rng(177 + 10 * nx + nt)
+    J = 1 + nx + nt
+    for trial in range(4):
+        z = rng.normal(size=J) * 0.8
+        ab = np.array([0.0218, 0.5, 1.5957, 1.1915, 1.0, 0.0, 2.3830]) + rng.normal(size=7) * 0.05
+        yb = rng.normal(size=J)
+        zb, abb, zb_y, abb_y = np.zeros(J), np.zeros(7), np.zeros(J), np.zeros(7)
+        assert harness.jet_harness(2, nx, nt, 1, _ptr(z), _ptr(ab), _ptr(yb), _ptr(zb), _ptr(abb)) == 0
+        assert harness.jet_harness_rational_vjp_y(nx, nt, _ptr(z), _ptr(ab), _ptr(yb), _ptr(zb_y), _ptr(abb_y)) == 0
+        np.testing.assert_allclose(zb_y, zb, rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(abb_y, abb, rtol=1e-13, atol=1e-14)
