@@ -122,6 +122,47 @@ PDR_HD void jet_mul_adj(const T* a, const T* b, const T* cbar, T* abar, T* bbar)
     }
 }
 
+// c = a*a: the symmetric half of the Cauchy product
+template <int NX, int NT, typename T>
+PDR_HD void jet_sqr(const T* a, T* c) {
+    c[0] = a[0] * a[0];
+    const T a0x2 = T(2) * a[0];
+#pragma unroll
+    for (int S = 0; S < 2; ++S) {
+        const int N = (S == 0) ? NX : NT;
+        const int off = (S == 0) ? 0 : NX;
+#pragma unroll
+        for (int k = 1; k <= N; ++k) {
+            T s = a0x2 * a[off + k];
+            T h = T(0);
+#pragma unroll
+            for (int i = 1; 2 * i < k; ++i) h += a[off + i] * a[off + k - i];
+            s += T(2) * h;
+            if (k % 2 == 0) s += a[off + k / 2] * a[off + k / 2];
+            c[off + k] = s;
+        }
+    }
+}
+
+// given cbar = dL/dc for c = a*a, accumulate abar += dL/da = 2 (cbar correlated with a)
+template <int NX, int NT, typename T>
+PDR_HD void jet_sqr_adj(const T* a, const T* cbar, T* abar) {
+    abar[0] += T(2) * cbar[0] * a[0];
+#pragma unroll
+    for (int S = 0; S < 2; ++S) {
+        const int N = (S == 0) ? NX : NT;
+        const int off = (S == 0) ? 0 : NX;
+#pragma unroll
+        for (int k = 1; k <= N; ++k) {
+            const T g = T(2) * cbar[off + k];
+            abar[0] += g * a[off + k];
+            abar[off + k] += g * a[0];
+#pragma unroll
+            for (int i = 1; i < k; ++i) abar[off + i] += g * a[off + k - i];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // tanh:  y' = (1 - y^2) z'.  With w = 1 - y^2:
 //     k y_k = sum_{j=1..k} j z_j w_{k-j},   w_k = -sum_{i=0..k} y_i y_{k-i}  (k >= 1)
@@ -304,7 +345,7 @@ PDR_HD void sin_vjp(const T* z, const T* ybar_in, T* zbar) {
 template <int NX, int NT, typename T>
 PDR_HD void rational_parts(const T* z, const T* ab, T* s2, T* s3, T* P, T* Q) {
     constexpr int J = 1 + NX + NT;
-    jet_mul<NX, NT, T>(z, z, s2);
+    jet_sqr<NX, NT, T>(z, s2);
     jet_mul<NX, NT, T>(s2, z, s3);
 #pragma unroll
     for (int i = 0; i < J; ++i) {
@@ -398,7 +439,7 @@ PDR_HD void rational_vjp_core(const T* z, const T* s2, const T* s3, const T* Q, 
     abbar[6] += gb2;
 
     jet_mul_adj<NX, NT, T>(s2, z, s3b, s2b, zbar);   // s3 = s2 * z
-    jet_mul_adj<NX, NT, T>(z, z, s2b, zbar, zbar);   // s2 = z * z
+    jet_sqr_adj<NX, NT, T>(z, s2b, zbar);            // s2 = z * z
 }
 
 template <int NX, int NT, typename T>
@@ -416,7 +457,7 @@ template <int NX, int NT, typename T>
 PDR_HD void rational_vjp_y(const T* z, const T* y, const T* ab, const T* ybar, T* zbar, T* abbar) {
     constexpr int J = 1 + NX + NT;
     T s2[J], s3[J], Q[J];
-    jet_mul<NX, NT, T>(z, z, s2);
+    jet_sqr<NX, NT, T>(z, s2);
     jet_mul<NX, NT, T>(s2, z, s3);
 #pragma unroll
     for (int i = 0; i < J; ++i) Q[i] = ab[5] * z[i] + ab[6] * s2[i];
