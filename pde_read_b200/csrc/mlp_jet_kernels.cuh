@@ -754,8 +754,14 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                                 act_fwd_row<ACT, NX, NT>(zl, ab_lo, yl);
                                 stash_store<J>(Zb + (size_t)i * HS + pt * J, yl);
                             }
-                            if (VJP_FROM_Y<ACT>::v) act_fwd_row<ACT, NX, NT>(z, ab, y);
-                            act_vjp_row<ACT, NX, NT>(z, y, ab, ybar, zbar, abbar);
+                            // y was overwritten by the parked ybar: tanh rebuilds it from the row (cheap series),
+                            // the others take the plain VJP, which evaluates the forward parts once
+                            if (ACT == ACT_TANH) {
+                                act_fwd_row<ACT, NX, NT>(z, ab, y);
+                                act_vjp_row<ACT, NX, NT>(z, y, ab, ybar, zbar, abbar);
+                            } else {
+                                act_vjp<ACT, NX, NT, float>(z, ab, ybar, zbar, abbar);
+                            }
                             stash_store<J>(Yb + (size_t)i * HS + pt * J, zbar);
                         }
                     }
