@@ -8,7 +8,13 @@
  *
  * Conventions
  *   - every pointer named d_* is DEVICE memory owned by the caller; the library never allocates
- *     or frees device memory and keeps no state between calls;
+ *     or frees device memory.  No result depends on an earlier call; what the library does keep for
+ *     the life of the process is launch bookkeeping (occupancy per kernel and shape, the dynamic
+ *     shared-memory limit per kernel, the compute-capability check per device; mutex / atomics,
+ *     safe from any host thread) and the pderead_debug_* switches (process-wide atomics meant for
+ *     tests and benchmarks: do not flip them while other threads are inside the library);
+ *   - every compute entry point returns PDEREAD_ERR_NOT_BLACKWELL on a device that is not
+ *     compute capability 10.x (the kernels are built for sm_100a only);
  *   - all tensors are contiguous row-major float32 unless stated otherwise;
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
  *   - every function returns 0 on success or a negative pderead_status; no exceptions cross.
@@ -118,7 +124,9 @@ int pderead_residual_forward(const pderead_net* sol, const pderead_net* pde, int
                              void* d_workspace, size_t workspace_bytes, void* stream);
 /* Collocation_Loss forward + Loss.backward() in one call (reference Test_Train.py:79-100 for the
  * collocation term): loss = sum(R^2)/M_total over the M local points (M_total >= M lets several
- * GPUs each take a shard; M_total = M on one GPU).  Adds sum(R^2) to *d_sum_sq and writes
+ * GPUs each take a shard; M_total = M on one GPU; M_total = 0 asks for the gradient of the UNSCALED
+ * sum(R^2), which the sharded host path divides by the all-reduced point count).  Adds sum(R^2) to
+ * *d_sum_sq and writes
  * grads = beta*grads + d(sum(R^2)/M_total)/d(parameter) for both networks.
  * If d_grad_resid != NULL it is used as d(loss)/dR [M] instead of 2R/M_total (PDE_Residual with an
  * arbitrary downstream loss). */
@@ -171,10 +179,20 @@ int pderead_rfe_gram(const double* d_G, const double* d_Atb, const double* d_btb
 int pderead_generate_points(const double* h_bounds, int dim, int64_t num_points, uint64_t seed,
                             uint64_t offset, float* d_points, void* stream);
 
+/* ---- sharded points (one process per GPU): the cross-rank part of Collocation_Loss ----------------
+ * mean(R^2) (reference Loss_Functions.py:65) and its gradient are sums over points, so every rank works on
+ * its slice (pderead_collocation_loss_grad with M_total = 0: unscaled sums) and ONE float32 SUM all-reduce of
+ * [gradients | tail4] finishes the step.  pack writes tail4 = {sum_sq hi, lo, M_local >> 12, M_local & 4095}
+ * (exact in float32 sums); unpack reads the reduced tail: d_out3 = {sum(R^2) over all ranks, total point
+ * count, scale / count} -- the factor the summed gradients are multiplied with (scale = 1 for the mean). */
+int pderead_loss_tail_pack(const double* d_sum_sq, int64_t M_local, float* d_tail4, void* stream);
+int pderead_loss_tail_unpack(const float* d_tail4, int64_t scale, double* d_out3, void* stream);
+
 /* ---- measurement helper ---------------------------------------------------------------------------
  * Runs a register-resident FFMA loop on every SM (`iters` dependent FMA chains per thread) so that
  * bench.py can measure the FP32 FMA peak that bounds this path.  variant 0: scalar FFMA,
- * variant 1: packed fma.rn.f32x2.  *h_flops receives the FLOP count of the launch. */
+ * variant 1: packed fma.rn.f32x2, variant 2: float64 DFMA (the bound of the Gram kernel).
+ * *h_flops receives the FLOP count of the launch. */
 int pderead_fma_peak_probe(int variant, int iters, float* d_sink, double* h_flops, void* stream);
 /* Hand the library `count` caller-created cudaEvent_t (host array).  Every kernel the following
  * calls on this host thread launch is followed by cudaEventRecord(events[i++], stream) until the

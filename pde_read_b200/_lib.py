@@ -85,6 +85,8 @@ PROTOTYPES = {
     "pderead_rfe_workspace_bytes": (c_size_t, [c_int]),
     "pderead_rfe_gram": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_void_p]),
+    "pderead_loss_tail_pack": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "pderead_loss_tail_unpack": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "pderead_generate_points": (c_int, [POINTER(c_double), c_int, c_int64, c_uint64, c_uint64, c_void_p, c_void_p]),
     "pderead_fma_peak_probe": (c_int, [c_int, c_int, c_void_p, POINTER(c_double), c_void_p]),
     "pderead_debug_stage_events": (c_int, [POINTER(c_void_p), c_int]),

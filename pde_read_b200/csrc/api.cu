@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "internal.h"
@@ -60,6 +61,23 @@ static thread_local cudaEvent_t* g_stage_events = nullptr;
 static thread_local int g_stage_count = 0, g_stage_next = 0;
 void stage_mark(cudaStream_t s) {
     if (g_stage_events && g_stage_next < g_stage_count) cudaEventRecord(g_stage_events[g_stage_next++], s);
+}
+
+// The kernels are built for sm_100a only: any other device gets PDEREAD_ERR_NOT_BLACKWELL instead of a launch
+// failure.  One attribute query per device and process (remembered in an atomic table).
+int check_device() {
+    static std::atomic<int> state[64];      // 0 unknown, 1 ok, 2 not Blackwell
+    int dev = 0;
+    PDR_CUDA_CHECK(cudaGetDevice(&dev));
+    const int slot = dev & 63;
+    int st = state[slot].load(std::memory_order_relaxed);
+    if (st == 0) {
+        int major = 0;
+        PDR_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+        st = (major == 10) ? 1 : 2;
+        state[slot].store(st, std::memory_order_relaxed);
+    }
+    return st == 1 ? PDEREAD_OK : PDEREAD_ERR_NOT_BLACKWELL;
 }
 
 int block_warps(int W) {
@@ -180,11 +198,46 @@ __global__ void tc_pack_weights_kernel(NetDev net, int mrows, int Kpad, int NB, 
     }
 }
 
+// ---- loss tail of the sharded step: [sum(R^2) hi, lo | point count hi, lo] as float32 pairs that ride at the
+// end of the packed gradient all-reduce (float32 SUM).  hi/lo of the sum keep ~48 bits; the count is split in
+// 12-bit / high parts so that every partial sum stays an exact integer in float32.
+__global__ void loss_tail_pack_kernel(const double* __restrict__ ss, long long M, float* __restrict__ tail) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double v = ss[0];
+        const float hi = (float)v;
+        tail[0] = hi;
+        tail[1] = (float)(v - (double)hi);
+        tail[2] = (float)(M >> 12);
+        tail[3] = (float)(M & 4095);
+    }
+}
+__global__ void loss_tail_unpack_kernel(const float* __restrict__ tail, double M_assumed, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double ssum = (double)tail[0] + (double)tail[1];
+        const double cnt = (double)tail[2] * 4096.0 + (double)tail[3];
+        out[0] = ssum;
+        out[1] = cnt;
+        out[2] = cnt > 0.0 ? M_assumed / cnt : 0.0;
+    }
+}
+
 __global__ void fma_probe_kernel(int variant, int iters, float* sink) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
     float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
     const float m = 0.999f, c = 1e-3f;
-    if (variant == 0) {
+    if (variant == 2) {
+        // float64 FMA chains (roofline denominator of the Gram kernel)
+        double d0 = a0, d1 = a1, d2 = a2, d3 = a3, d4 = a4, d5 = a5, d6 = a6, d7 = a7;
+        const double dm = 0.999, dc = 1e-3;
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                d0 = fma(d0, dm, dc); d1 = fma(d1, dm, dc); d2 = fma(d2, dm, dc); d3 = fma(d3, dm, dc);
+                d4 = fma(d4, dm, dc); d5 = fma(d5, dm, dc); d6 = fma(d6, dm, dc); d7 = fma(d7, dm, dc);
+            }
+        }
+        a0 = (float)(d0 + d1 + d2 + d3); a1 = (float)(d4 + d5 + d6 + d7);
+    } else if (variant == 0) {
         for (int i = 0; i < iters; ++i) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -257,6 +310,7 @@ __global__ void generate_points_kernel(BoundsDev bd, int dim, long long n, unsig
 // ---------------------------------------------------------------------------------------------
 static int to_netdev(const pderead_net* n, NetDev* out) {
     if (n == nullptr) return PDEREAD_ERR_BAD_ARGUMENT;
+    { const int rc_ = check_device(); if (rc_ != PDEREAD_OK) return rc_; }
     if (n->num_hidden_layers < 1 || n->num_hidden_layers > MAXL) return PDEREAD_ERR_UNSUPPORTED_NET;
     if (n->width < 1 || n->input_dim < 1 || n->input_dim > MAXD) return PDEREAD_ERR_UNSUPPORTED_NET;
     if (n->activation < 0 || n->activation > 2) return PDEREAD_ERR_UNSUPPORTED_NET;
@@ -338,15 +392,18 @@ static bool order_supported(int nx, int nt) {
 // tensor core truncates inside its accumulation and 3xTF32 lands at ~1e-6 relative error per network
 // instead of fp32's ~1e-7, which the residual cancellation of a trained network amplifies in the
 // gradients.  2 = force: tensor cores wherever the shape is supported.
-static int g_tc_mode = -1;
+static std::atomic<int> g_tc_mode{-1};
 static int tc_mode() {
-    if (g_tc_mode < 0) {
+    int m = g_tc_mode.load(std::memory_order_relaxed);
+    if (m < 0) {
         const char* e = getenv("PDEREAD_TC");
-        g_tc_mode = 1;
-        if (e && (e[0] == 'o' || e[0] == 'O' || e[0] == '0')) g_tc_mode = 0;
-        if (e && (e[0] == 'f' || e[0] == 'F' || e[0] == '2')) g_tc_mode = 2;
+        m = 1;
+        if (e && (e[0] == 'o' || e[0] == 'O' || e[0] == '0')) m = 0;
+        if (e && (e[0] == 'f' || e[0] == 'F' || e[0] == '2')) m = 2;
+        int expect = -1;
+        if (!g_tc_mode.compare_exchange_strong(expect, m)) m = expect;
     }
-    return g_tc_mode;
+    return m;
 }
 static bool tc_allowed(const NetDev& n, bool gradient_path) {
     const int m = tc_mode();
@@ -734,9 +791,8 @@ int pderead_debug_stage_events(void* const* events, int count) {
 int pderead_debug_stage_events_recorded(void) { return g_stage_next; }
 
 int pderead_debug_set_tensor_cores(int mode) {
-    const int prev = tc_mode();
-    g_tc_mode = (mode < 0 || mode > 2) ? 1 : mode;
-    return prev;
+    (void)tc_mode();
+    return g_tc_mode.exchange((mode < 0 || mode > 2) ? 1 : mode);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1049,7 +1105,7 @@ static int residual_impl(const pderead_net* sol, const pderead_net* pde, int m, 
     if ((rc = to_netdev(pde, &N))) return rc;
     if (!order_supported(n, m) || n < 1 || m < 1) return PDEREAD_ERR_UNSUPPORTED_ORDER;
     if (U.din != 2 || N.din != n + 1) return PDEREAD_ERR_UNSUPPORTED_NET;
-    if (M <= 0 || !d_coords || !ws || M_total < M) return PDEREAD_ERR_BAD_ARGUMENT;
+    if (M <= 0 || !d_coords || !ws || (M_total != 0 && M_total < M)) return PDEREAD_ERR_BAD_ARGUMENT;
     const int J = jet_len(n, m);
     const GradLayout lu = make_layout(U), ln = make_layout(N);
     SegmentTable tu, tn;
@@ -1125,7 +1181,7 @@ static int residual_impl(const pderead_net* sol, const pderead_net* pde, int m, 
         fn.resid_out = d_resid ? d_resid + lo : nullptr;
         fn.seed_out = backward ? seedN : nullptr;
         fn.grad_resid = d_grad_resid ? d_grad_resid + lo : nullptr;
-        fn.seed_scale = (float)(2.0 / (double)M_total);
+        fn.seed_scale = M_total > 0 ? (float)(2.0 / (double)M_total) : 2.f;   // M_total = 0: unscaled sum(R^2)
         fn.sumsq = d_sum_sq;
         if ((rc = plan_launch(pde->activation, 0, 0, fN, fn, s))) return rc;
         if (backward) {
@@ -1244,6 +1300,25 @@ int pderead_extraction_gram(const pderead_net* sol, const pderead_net* pde, int 
 }
 
 // ------------------------------------------------------------------------------------------
+// sharded step: loss + point count in the tail of the gradient all-reduce
+// ------------------------------------------------------------------------------------------
+int pderead_loss_tail_pack(const double* d_sum_sq, int64_t M_local, float* d_tail4, void* stream) {
+    if (!d_sum_sq || !d_tail4 || M_local < 0) return PDEREAD_ERR_BAD_ARGUMENT;
+    { const int rc_ = check_device(); if (rc_ != PDEREAD_OK) return rc_; }
+    loss_tail_pack_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_sum_sq, (long long)M_local, d_tail4);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    return PDEREAD_OK;
+}
+
+int pderead_loss_tail_unpack(const float* d_tail4, int64_t M_assumed, double* d_out3, void* stream) {
+    if (!d_tail4 || !d_out3 || M_assumed < 0) return PDEREAD_ERR_BAD_ARGUMENT;
+    { const int rc_ = check_device(); if (rc_ != PDEREAD_OK) return rc_; }
+    loss_tail_unpack_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_tail4, (double)M_assumed, d_out3);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    return PDEREAD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // points, probe
 // ------------------------------------------------------------------------------------------
 int pderead_generate_points(const double* h_bounds, int dim, int64_t num_points, uint64_t seed, uint64_t offset,
@@ -1251,6 +1326,7 @@ int pderead_generate_points(const double* h_bounds, int dim, int64_t num_points,
     if (!h_bounds || dim < 1 || dim > MAXD || num_points < 0 || (num_points > 0 && !d_points))
         return PDEREAD_ERR_BAD_ARGUMENT;
     if (num_points == 0) return PDEREAD_OK;
+    { const int rc_ = check_device(); if (rc_ != PDEREAD_OK) return rc_; }
     BoundsDev bd;
     for (int d = 0; d < dim; ++d) {
         if (h_bounds[2 * d] > h_bounds[2 * d + 1]) return PDEREAD_ERR_BAD_ARGUMENT;   // reference Points.py:45-46
@@ -1265,7 +1341,8 @@ int pderead_generate_points(const double* h_bounds, int dim, int64_t num_points,
 }
 
 int pderead_fma_peak_probe(int variant, int iters, float* d_sink, double* h_flops, void* stream) {
-    if (!d_sink || iters < 1 || variant < 0 || variant > 1) return PDEREAD_ERR_BAD_ARGUMENT;
+    if (!d_sink || iters < 1 || variant < 0 || variant > 2) return PDEREAD_ERR_BAD_ARGUMENT;
+    { const int rc_ = check_device(); if (rc_ != PDEREAD_OK) return rc_; }
     int dev = 0, sms = 0;
     PDR_CUDA_CHECK(cudaGetDevice(&dev));
     PDR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

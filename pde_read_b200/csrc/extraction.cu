@@ -18,9 +18,7 @@ namespace pdr {
 
 constexpr int MAXC = PDEREAD_MAX_LIBRARY_COLUMNS;
 constexpr int MAXK = 8;
-constexpr int GB = 64;   // edge of the Gram block one CTA accumulates
 constexpr int GP = 32;   // points per tile
-constexpr int GS = GP + 1;
 
 // column c (degree k >= 1) = column parent[c] (its length k-1 prefix) times D[last[c]]: the same
 // left-to-right product order as the reference's inner loop (Extraction.py:364-366).
@@ -110,39 +108,50 @@ __global__ void __launch_bounds__(256) library_dense_kernel(LibTable t, const fl
     }
 }
 
-// Fused library + Gram.  Grid = (point slices, block pairs bi <= bj of the augmented Gram
-// [A | b]^T [A | b]).  Each CTA keeps a 64x64 float64 block in registers (4x4 per thread) over
-// all its tiles and adds it to the global result once at the end.
-template <bool DENSE>
-__global__ void __launch_bounds__(256) gram_kernel(LibTable t, const float* __restrict__ src, const float* __restrict__ bvec,
-                                                   long long M, int nblk, double* __restrict__ G,
-                                                   double* __restrict__ Atb, double* __restrict__ btb) {
+// Fused library + Gram of the augmented matrix [A | b] (CA = C + 1 columns), upper triangle only.
+//
+// The columns are cut into groups of T; a thread owns one T x T tile (gi <= gj) of [A|b]^T [A|b] in float64
+// registers over all the point tiles of its CTA, so the symmetric half is never computed (C = 56: 1980 DFMA
+// per point instead of the 4096 of a full 64 x 64 block).  A CTA covers `ntile_cta` consecutive tiles of the
+// list (blockIdx.y selects the chunk; large libraries need several chunks for the register file) and SUB
+// sub-slices of the points of a tile (warp-uniform), and adds its result to the global system once at the end.
+// Shared layout of the widened tile: AD[group][row in group][point], strides (T*GP + 1, GP, 1) doubles: the odd
+// group stride spreads the groups a warp touches over the 16 8-byte banks.
+template <bool DENSE, int T>
+__global__ void __launch_bounds__(T == 8 ? 192 : 256, 2) gram_kernel(LibTable t, const float* __restrict__ src, const float* __restrict__ bvec,
+                                                   long long M, int ngroups, int ntile_total, int ntile_cta, int sub,
+                                                   double* __restrict__ G, double* __restrict__ Atb,
+                                                   double* __restrict__ btb) {
     extern __shared__ __align__(16) unsigned char smraw[];
+    constexpr int GST = T * GP + 1;
     const int C = t.C, CA = C + 1;
     const int nd = t.n + 1;
-    double* Ai = reinterpret_cast<double*>(smraw);   // [GB][GS]
-    double* Aj = Ai + GB * GS;                       // [GB][GS]
-    float* LIB = reinterpret_cast<float*>(Aj + GB * GS);   // [C][GP]
-    float* D = LIB + (size_t)C * GP;                 // [(n+1)][GP]
-    float* MASK = D + nd * GP;                       // [GP]
-    float* BV = MASK + GP;                           // [GP]
+    double* AD = reinterpret_cast<double*>(smraw);                    // [ngroups][T][GP] (+1 per group)
+    float* LIB = reinterpret_cast<float*>(AD + (size_t)ngroups * GST);   // [C][GP]
+    float* D = LIB + (size_t)C * GP;                                  // [(n+1)][GP]
+    float* MASK = D + nd * GP;                                        // [GP]
+    float* BV = MASK + GP;                                            // [GP]
 
-    // decode block pair
-    int bi = 0, bj = 0;
-    {
-        int rem = blockIdx.y;
-        for (bi = 0; bi < nblk; ++bi) {
-            const int cnt = nblk - bi;
-            if (rem < cnt) { bj = bi + rem; break; }
+    // this thread's tile: index into the list of (gi <= gj) pairs, row-major over gi
+    const int tiles_pad = (ntile_cta + 31) & ~31;
+    const int my_sub = threadIdx.x / tiles_pad;
+    const int tl = threadIdx.x - my_sub * tiles_pad;
+    const int tile_id = blockIdx.y * ntile_cta + tl;
+    const bool has_tile = (tl < ntile_cta) && (tile_id < ntile_total) && (my_sub < sub);
+    int gi = 0, gj = 0;
+    if (has_tile) {
+        int rem = tile_id;
+        for (gi = 0; gi < ngroups; ++gi) {
+            const int cnt = ngroups - gi;
+            if (rem < cnt) { gj = gi + rem; break; }
             rem -= cnt;
         }
     }
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double acc[4][4];
+    double acc[T][T];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < T; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        for (int b = 0; b < T; ++b) acc[a][b] = 0.0;
 
     const long long tiles = (M + GP - 1) / GP;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -166,73 +175,132 @@ __global__ void __launch_bounds__(256) gram_kernel(LibTable t, const float* __re
             __syncthreads();
             build_library_tile(t, D, LIB, MASK);
         }
-        // widen the two column blocks to float64
-        for (int idx = threadIdx.x; idx < GB * GP; idx += blockDim.x) {
-            const int r = idx / GP, p = idx - r * GP;
-            const int ci = bi * GB + r, cj = bj * GB + r;
-            Ai[r * GS + p] = (ci < C) ? (double)LIB[ci * GP + p] : (ci == C ? (double)BV[p] : 0.0);
-            Aj[r * GS + p] = (cj < C) ? (double)LIB[cj * GP + p] : (cj == C ? (double)BV[p] : 0.0);
+        // widen to float64 (column C = b, columns beyond = 0)
+        for (int idx = threadIdx.x; idx < ngroups * T * GP; idx += blockDim.x) {
+            const int c = idx / GP, p = idx - c * GP;
+            const int g = c / T, r = c - g * T;
+            AD[(size_t)g * GST + r * GP + p] = (c < C) ? (double)LIB[c * GP + p] : (c == C ? (double)BV[p] : 0.0);
         }
         __syncthreads();
-#pragma unroll 4
-        for (int p = 0; p < GP; ++p) {
-            double av[4], bv[4];
+        if (has_tile) {
+            const double* pa = AD + (size_t)gi * GST;
+            const double* pb = AD + (size_t)gj * GST;
+#pragma unroll(T == 8 ? 1 : 2)
+            for (int p = my_sub; p < GP; p += sub) {
+                double av[T], bv[T];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) av[a] = Ai[(ty + 16 * a) * GS + p];
+                for (int a = 0; a < T; ++a) av[a] = pa[a * GP + p];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) bv[b] = Aj[(tx + 16 * b) * GS + p];
+                for (int b = 0; b < T; ++b) bv[b] = pb[b * GP + p];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < T; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+                    for (int b = 0; b < T; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+            }
         }
         __syncthreads();
     }
 
+    // combine the sub-slices in shared memory (reuses AD), then one float64 atomic per entry and CTA
+    double* RED = AD;      // [tiles_pad][T*T] (host sizes the buffer for it)
+    for (int s = 1; s < sub; ++s) {
+        if (has_tile && my_sub == s) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < T; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int i = bi * GB + ty + 16 * a, j = bj * GB + tx + 16 * b;
-            if (i >= CA || j >= CA) continue;
-            const double v = acc[a][b];
-            if (i < C && j < C) {
-                atomicAdd(&G[(size_t)i * C + j], v);
-                if (bi != bj) atomicAdd(&G[(size_t)j * C + i], v);
-            } else if (i < C && j == C) {
-                atomicAdd(&Atb[i], v);
-            } else if (i == C && j == C) {
-                atomicAdd(btb, v);
-            }   // (i == C, j < C) duplicates (j, C) of the same diagonal block: skipped
+                for (int b = 0; b < T; ++b) RED[(size_t)(a * T + b) * tiles_pad + tl] = acc[a][b];
         }
+        __syncthreads();
+        if (has_tile && my_sub == 0) {
+#pragma unroll
+            for (int a = 0; a < T; ++a)
+#pragma unroll
+                for (int b = 0; b < T; ++b) acc[a][b] += RED[(size_t)(a * T + b) * tiles_pad + tl];
+        }
+        __syncthreads();
+    }
+    if (has_tile && my_sub == 0) {
+#pragma unroll
+        for (int a = 0; a < T; ++a)
+#pragma unroll
+            for (int b = 0; b < T; ++b) {
+                const int i = gi * T + a, j = gj * T + b;
+                if (i >= CA || j >= CA || j < i) continue;          // (diagonal tiles: upper triangle only)
+                const double v = acc[a][b];
+                if (j < C) {
+                    atomicAdd(&G[(size_t)i * C + j], v);
+                    if (i != j) atomicAdd(&G[(size_t)j * C + i], v);
+                } else if (i < C) {
+                    atomicAdd(&Atb[i], v);
+                } else {
+                    atomicAdd(btb, v);
+                }
+            }
+    }
 }
 
-static size_t gram_smem_bytes(const LibTable& t) {
-    return sizeof(double) * 2 * GB * GS + sizeof(float) * ((size_t)t.C * GP + (t.n + 1) * GP + 2 * GP);
+struct GramGeom {
+    int T, ngroups, ntile, nchunk, ntile_cta, sub, threads;
+    size_t smem;
+};
+
+static GramGeom gram_geometry(const LibTable& t) {
+    const int CA = t.C + 1;
+    GramGeom best;
+    memset(&best, 0, sizeof(best));
+    long best_work = -1;
+    const int Ts[2] = {8, 6};
+    for (int k = 0; k < 2; ++k) {
+        GramGeom g;
+        g.T = Ts[k];
+        g.ngroups = (CA + g.T - 1) / g.T;
+        g.ntile = g.ngroups * (g.ngroups + 1) / 2;
+        const long work = (long)g.ntile * g.T * g.T;            // DFMA per point
+        const int cap = (g.T == 8) ? 192 : 256;                  // tiles per CTA (register file: 64 / 36 accumulators)
+        g.nchunk = (g.ntile + cap - 1) / cap;
+        g.ntile_cta = (g.ntile + g.nchunk - 1) / g.nchunk;
+        const int pad = (g.ntile_cta + 31) & ~31;
+        g.sub = cap / pad;
+        if (g.sub < 1) g.sub = 1;
+        if (g.sub > 8) g.sub = 8;
+        g.threads = pad * g.sub;
+        const size_t ad = sizeof(double) * (size_t)g.ngroups * (g.T * GP + 1);
+        const size_t red = g.sub > 1 ? sizeof(double) * (size_t)pad * g.T * g.T : 0;
+        g.smem = (ad > red ? ad : red) + sizeof(float) * ((size_t)t.C * GP + (t.n + 1) * GP + 2 * GP) + 16;
+        if (best_work < 0 || work < best_work) {
+            best_work = work;
+            best = g;
+        }
+    }
+    return best;
 }
 
 int gram_launch(const LibTable& t, bool dense, const float* src, const float* b, long long M, double* G, double* Atb,
                 double* btb, cudaStream_t s) {
     if (M <= 0) return PDEREAD_OK;
-    const int CA = t.C + 1;
-    const int nblk = (CA + GB - 1) / GB;
-    const int npairs = nblk * (nblk + 1) / 2;
+    { const int rc_ = check_device(); if (rc_ != PDEREAD_OK) return rc_; }
+    const GramGeom g = gram_geometry(t);
     int dev = 0, sms = 0;
     PDR_CUDA_CHECK(cudaGetDevice(&dev));
     PDR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long tiles = (M + GP - 1) / GP;
-    long long slices = ((long long)sms * 2 + npairs - 1) / npairs;
+    long long slices = ((long long)sms * 2 + g.nchunk - 1) / g.nchunk;
     if (slices > tiles) slices = tiles;
     if (slices < 1) slices = 1;
-    const size_t smem = gram_smem_bytes(t);
-    dim3 grid((unsigned)slices, (unsigned)npairs);
+    dim3 grid((unsigned)slices, (unsigned)g.nchunk);
+#define PDR_GRAM_LAUNCH(DENSE_, T_)                                                                                   \
+    do {                                                                                                              \
+        const int rc_ = ensure_dynamic_smem((const void*)gram_kernel<DENSE_, T_>, g.smem);                            \
+        if (rc_ != PDEREAD_OK) return rc_;                                                                            \
+        gram_kernel<DENSE_, T_><<<grid, g.threads, g.smem, s>>>(t, src, b, M, g.ngroups, g.ntile, g.ntile_cta, g.sub, \
+                                                                G, Atb, btb);                                         \
+    } while (0)
     if (dense) {
-        { const int rc_ = ensure_dynamic_smem((const void*)gram_kernel<true>, smem); if (rc_ != PDEREAD_OK) return rc_; }
-        gram_kernel<true><<<grid, 256, smem, s>>>(t, src, b, M, nblk, G, Atb, btb);
+        if (g.T == 8) PDR_GRAM_LAUNCH(true, 8); else PDR_GRAM_LAUNCH(true, 6);
     } else {
-        { const int rc_ = ensure_dynamic_smem((const void*)gram_kernel<false>, smem); if (rc_ != PDEREAD_OK) return rc_; }
-        gram_kernel<false><<<grid, 256, smem, s>>>(t, src, b, M, nblk, G, Atb, btb);
+        if (g.T == 8) PDR_GRAM_LAUNCH(false, 8); else PDR_GRAM_LAUNCH(false, 6);
     }
+#undef PDR_GRAM_LAUNCH
     PDR_CUDA_CHECK(cudaGetLastError());
     stage_mark(s);
     return PDEREAD_OK;
@@ -247,140 +315,264 @@ int library_gram_launch(const float* dxn, const float* b, long long M, int n, in
 }
 
 // ---------------------------------------------------------------------------------------------
-// RFE on the Gram system, one CTA.
+// RFE on the Gram system, one CTA, float64: the sweep operator.
 //
-// With unit-norm columns A_s = A diag(1/||A_i||) the normal equations of step j are
-//   Gs[S,S] x = cs[S],   Gs = G / (norm norm^T),  cs = A^T b / norm,
-// solved by Cholesky in float64 with the right-hand side carried as an extra row, so that
-// w = L^-1 cs and ||b - A_s x||^2 = b^T b - w^T w.  (The reference solves the same least-squares
-// problem with LAPACK dgelsd on the tall matrix, Extraction.py:464.)
+// With unit-norm columns A_s = A diag(1/||A_i||) (reference Extraction.py:443-453) step j of the reference solves
+//   min ||b - A_s[:, S] x||   (numpy.linalg.lstsq, Extraction.py:464)
+// on the surviving set S.  On the augmented scaled Gram matrix  T = [[Gs, cs], [cs^T, b^T b]]  the sweep
+//   SWP(k): d = T_kk;  T_ij -= T_ik T_kj / d (i, j != k);  T_ik = T_ki = T_ik / d;  T_kk = -1 / d
+// applied to every k in S leaves  T_SS = -Gs_SS^-1,  T_S,rhs = x  and  T_rhs,rhs = ||b - A_s x||^2, and removing
+// feature q from S is the reverse sweep, which on the kept entries is the same rank-1 update
+//   T_ij -= T_iq T_qj / T_qq.
+// So the kernel sweeps all C features in once (largest remaining diagonal first; a pivot below PIV_TOL means the
+// column is numerically dependent on those already in: it is never swept, keeps coefficient 0 and leaves first)
+// and then performs one rank-1 downdate per elimination: O(C^3) in total, every step fully parallel, two block
+// barriers per step.  Ties in |x| go to the lowest index and the comparison is done on the float32 values, as in the
+// reference (Extraction.py:467-476 scans the float32 X with a strict '<').
+//
+// Difference from the reference for rank-deficient libraries: dgelsd returns the minimum-norm solution (a
+// duplicated column shares its coefficient with its twin and both survive until that share is the smallest
+// entry); here the later twin is dropped at once with coefficient 0 and the eliminations that follow are those
+// of the library without it.  A zero column gets coefficient 0 (the reference divides by its zero norm -> NaN).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rfe_kernel(const double* __restrict__ G, const double* __restrict__ Atb,
-                                                  const double* __restrict__ btb, int C, float* __restrict__ X,
-                                                  float* __restrict__ residual, int* __restrict__ order,
-                                                  int* __restrict__ rank, float* __restrict__ change,
-                                                  double* __restrict__ gws, int use_smem) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    const int LS = (C + 1) | 1;                  // odd row stride (doubles): conflict-free column walks
-    double* Lm = use_smem ? reinterpret_cast<double*>(smraw) : gws;          // [(C+1)][LS]
-    double* small = use_smem ? Lm + (size_t)(C + 1) * LS : reinterpret_cast<double*>(smraw);
-    double* nrm = small;                         // [C]
-    double* tmp = nrm + C;                       // [C+1]
-    double* xs = tmp + C + 1;                    // [C]
-    double* wv = xs + C;                         // [C]
-    int* act = reinterpret_cast<int*>(wv + C);   // [C]
-    int* alive = act + C;                        // [C]
-    __shared__ int s_m, s_drop;
-    __shared__ double s_piv;
+constexpr double RFE_PIV_TOL = 1e-13;
 
-    const int tid = threadIdx.x, nt = blockDim.x;
+struct ArgBest {
+    float v;
+    int i;
+};
+// lexicographic (value, index) minimum over the warp
+__device__ __forceinline__ ArgBest warp_argmin(ArgBest b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, b.v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, b.i, o);
+        if (ov < b.v || (ov == b.v && oi < b.i)) { b.v = ov; b.i = oi; }
+    }
+    return b;
+}
+// every warp combines the per-warp partial results itself (no barrier, no serial section)
+__device__ __forceinline__ ArgBest block_argmin_from_partials(const float* pv, const int* pi, int nwarps) {
+    const int lane = threadIdx.x & 31;
+    ArgBest b;
+    b.v = lane < nwarps ? pv[lane] : INFINITY;
+    b.i = lane < nwarps ? pi[lane] : 0x7fffffff;
+    return warp_argmin(b);
+}
+
+__global__ void __launch_bounds__(1024) rfe_kernel(const double* __restrict__ G, const double* __restrict__ Atb,
+                                                   const double* __restrict__ btb, int C, float* __restrict__ X,
+                                                   float* __restrict__ residual, int* __restrict__ order,
+                                                   int* __restrict__ rank, float* __restrict__ change,
+                                                   double* __restrict__ gws, int use_smem) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int LD = C + 1;
+    double* Tm = use_smem ? reinterpret_cast<double*>(smraw) : gws;          // [(C+1)][(C+1)]
+    double* small = use_smem ? Tm + (size_t)LD * LD : reinterpret_cast<double*>(smraw);
+    double* nrm = small;                         // [C]
+    double* hv = nrm + C;                        // [C+1] pivot row of the current step
+    double* dg = hv + C + 1;                     // [C]   running diagonal (forward phase)
+    double* xs0 = dg + C;                        // [C]   coefficients of the active set, compact (double-buffered)
+    double* xs1 = xs0 + C;
+    int* act0 = reinterpret_cast<int*>(xs1 + C); // [C]   active features, ascending, compact (double-buffered)
+    int* act1 = act0 + C;
+    int* swept = act1 + C;                       // [C]
+    float* pv = reinterpret_cast<float*>(swept + C);   // [32] per-warp partial results of the arg-min / arg-max
+    int* pi = reinterpret_cast<int*>(pv + 32);         // [32]
+
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const float inv_ld = 1.0f / (float)LD;
+
     for (int i = tid; i < C; i += nt) {
-        nrm[i] = sqrt(G[(size_t)i * C + i]);
-        alive[i] = 1;
+        const double g = G[(size_t)i * C + i];
+        nrm[i] = g > 0.0 ? sqrt(g) : 0.0;
+        swept[i] = 0;
     }
     for (int i = tid; i < C * C; i += nt) X[i] = 0.f;
     __syncthreads();
+    for (int idx = tid; idx < LD * LD; idx += nt) {
+        const int i = (int)(((float)idx + 0.5f) * inv_ld), j = idx - i * LD;
+        double v;
+        if (i < C && j < C) {
+            const double den = nrm[i] * nrm[j];
+            v = den > 0.0 ? G[(size_t)i * C + j] / den : 0.0;
+        } else if (i < C || j < C) {
+            const int c = i < C ? i : j;
+            v = nrm[c] > 0.0 ? Atb[c] / nrm[c] : 0.0;
+        } else {
+            v = btb[0];
+        }
+        Tm[idx] = v;
+    }
     const double bb = btb[0];
+    // arg-max of the diagonal for the first pivot (negated: the helpers are arg-min)
+    {
+        ArgBest b;
+        b.v = INFINITY; b.i = 0x7fffffff;
+        for (int i = tid; i < C; i += nt) {
+            const double d = nrm[i] > 0.0 ? 1.0 : 0.0;
+            dg[i] = d;
+            const float v = -(float)d;
+            if (v < b.v || (v == b.v && i < b.i)) { b.v = v; b.i = i; }
+        }
+        b = warp_argmin(b);
+        if (lane == 0) { pv[warp] = b.v; pi[warp] = b.i; }
+    }
+    __syncthreads();
 
-    for (int step = 0; step < C; ++step) {
-        if (tid == 0) {
-            int m = 0;
-            for (int i = 0; i < C; ++i)
-                if (alive[i]) act[m++] = i;
-            s_m = m;
-        }
+    // ---- forward: sweep the features in, best-conditioned first ----
+    int nswept = 0;
+    for (int s = 0; s < C; ++s) {
+        const ArgBest pb = block_argmin_from_partials(pv, pi, nwarps);
+        const int k = pb.i;
+        if (k < 0 || k >= C) break;
+        const double d = dg[k];
+        if (!(d >= RFE_PIV_TOL)) break;              // everything left is numerically dependent on the swept set
+        for (int j = tid; j < LD; j += nt) hv[j] = Tm[(size_t)k * LD + j];
         __syncthreads();
-        const int m = s_m;
-        // scaled Gram of the active set (lower triangle) with the scaled right-hand side as row m
-        for (int idx = tid; idx < (m + 1) * m; idx += nt) {
-            const int a = idx / m, b = idx - a * m;
-            if (a < m) {
-                if (b <= a) {
-                    const int ia = act[a], ib = act[b];
-                    const double den = nrm[ia] * nrm[ib];
-                    Lm[(size_t)a * LS + b] = den > 0.0 ? G[(size_t)ia * C + ib] / den : (a == b ? 1.0 : 0.0);
-                }
-            } else {
-                const int ib = act[b];
-                Lm[(size_t)m * LS + b] = nrm[ib] > 0.0 ? Atb[ib] / nrm[ib] : 0.0;
+        const double inv_d = 1.0 / d;
+        for (int idx = tid; idx < LD * LD; idx += nt) {
+            const int i = (int)(((float)idx + 0.5f) * inv_ld), j = idx - i * LD;
+            double v;
+            if (i == k) v = (j == k) ? -inv_d : hv[j] * inv_d;
+            else if (j == k) v = hv[i] * inv_d;
+            else v = fma(-hv[i] * inv_d, hv[j], Tm[idx]);
+            Tm[idx] = v;
+        }
+        ArgBest b;
+        b.v = INFINITY; b.i = 0x7fffffff;
+        for (int i = tid; i < C; i += nt) {
+            if (i == k) swept[i] = 1;
+            else if (!swept[i]) {
+                const double nd2 = fma(-hv[i] * inv_d, hv[i], dg[i]);
+                dg[i] = nd2;
+                const float v = -(float)nd2;
+                if (v < b.v || (v == b.v && i < b.i)) { b.v = v; b.i = i; }
             }
         }
-        __syncthreads();
-        // left-looking Cholesky, rows k..m (row m = right-hand side)
-        for (int k = 0; k < m; ++k) {
-            for (int i = k + tid; i <= m; i += nt) {
-                double s = Lm[(size_t)i * LS + k];
-                const double* ri = Lm + (size_t)i * LS;
-                const double* rk = Lm + (size_t)k * LS;
-                for (int t2 = 0; t2 < k; ++t2) s = fma(-ri[t2], rk[t2], s);
-                tmp[i] = s;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                const double d2 = tmp[k];
-                // the scaled Gram has a unit diagonal: a pivot this small means the column is
-                // numerically dependent on the earlier ones -> freeze it at zero
-                s_piv = (d2 > 1e-13) ? sqrt(d2) : 1e150;
-            }
-            __syncthreads();
-            const double d = s_piv;
-            for (int i = k + tid; i <= m; i += nt) Lm[(size_t)i * LS + k] = (i == k) ? d : tmp[i] / d;
-            __syncthreads();
-        }
-        // w = row m;  back substitution L^T x = w
-        for (int i = tid; i < m; i += nt) wv[i] = Lm[(size_t)m * LS + i];
-        __syncthreads();
-        double ww = 0.0;
-        if (tid == 0)
-            for (int i = 0; i < m; ++i) ww = fma(wv[i], wv[i], ww);
-        for (int k = m - 1; k >= 0; --k) {
-            if (tid == 0) xs[k] = wv[k] / Lm[(size_t)k * LS + k];
-            __syncthreads();
-            const double xk = xs[k];
-            for (int t2 = tid; t2 < k; t2 += nt) wv[t2] = fma(-Lm[(size_t)k * LS + t2], xk, wv[t2]);
-            __syncthreads();
-        }
-        // record the candidate, pick the feature to drop: smallest |x| in float32, first index wins
-        // ties (reference Extraction.py:467-476 compares the float32 entries of X with strict '<')
-        for (int a = tid; a < m; a += nt) {
-            const int ia = act[a];
-            const float xf = (float)xs[a];
-            X[(size_t)ia * C + step] = xf / (float)nrm[ia];
-        }
-        if (tid == 0) {
-            int best = 0;
-            float bv = fabsf((float)xs[0]);
-            for (int a = 1; a < m; ++a) {
-                const float v = fabsf((float)xs[a]);
-                if (v < bv) { bv = v; best = a; }
-            }
-            s_drop = act[best];
-            alive[act[best]] = 0;
-            order[step] = act[best];
-            const double r2 = bb - ww;
-            residual[step] = (float)sqrt(r2 > 0.0 ? r2 : 0.0);
-        }
+        b = warp_argmin(b);
+        if (lane == 0) { pv[warp] = b.v; pi[warp] = b.i; }   // (this step's partials were consumed before the barrier above)
+        ++nswept;
         __syncthreads();
     }
-    if (tid == 0) {
-        residual[C] = (float)sqrt(bb > 0.0 ? bb : 0.0);
-        // Rank_Candidate_Solutions: relative jump, ascending selection sort carrying indices
-        for (int i = 0; i < C; ++i) {
-            change[i] = (residual[i + 1] - residual[i]) / residual[i];
-            rank[i] = i;
+
+    // ---- compact active list (ascending), coefficients, frozen list ----
+    for (int i = tid; i < C; i += nt) {
+        int pos = 0;
+        for (int u = 0; u < i; ++u) pos += swept[u];
+        if (swept[i]) {
+            act0[pos] = i;
+            xs0[pos] = Tm[(size_t)C * LD + i];
+        } else {
+            act1[i - pos] = i;                       // frozen features, ascending (act1 is free until the first swap)
         }
+    }
+    __syncthreads();
+    const int nfrozen = C - nswept;
+    double r2 = Tm[(size_t)C * LD + C];
+    int m = nswept;
+    int step = 0;
+    // frozen features leave first, one per step, with the candidate solution unchanged
+    for (; step < nfrozen; ++step) {
+        for (int a = tid; a < m; a += nt) X[(size_t)act0[a] * C + step] = (float)xs0[a] / (float)nrm[act0[a]];
+        if (tid == 0) {
+            residual[step] = (float)sqrt(r2 > 0.0 ? r2 : 0.0);
+            order[step] = act1[step];
+        }
+    }
+    __syncthreads();
+    // first arg-min over |x| (float32)
+    {
+        ArgBest b;
+        b.v = INFINITY; b.i = 0x7fffffff;
+        for (int a = tid; a < m; a += nt) {
+            const float v = fabsf((float)xs0[a]);
+            if (v < b.v || (v == b.v && a < b.i)) { b.v = v; b.i = a; }
+        }
+        b = warp_argmin(b);
+        if (lane == 0) { pv[warp] = b.v; pi[warp] = b.i; }
+    }
+    __syncthreads();
+
+    // ---- reverse: one rank-1 downdate per elimination ----
+    double* xs = xs0; double* xn = xs1;
+    int* act = act0; int* actn = act1;
+    for (; step < C; ++step) {
+        const ArgBest pb = block_argmin_from_partials(pv, pi, nwarps);
+        const int aq = pb.i;                          // position of the feature to drop in the compact list
+        const int q = act[aq];
+        const double xq = xs[aq];
+        const double d = Tm[(size_t)q * LD + q];      // = -(Gs_SS^-1)_qq < 0
+        for (int a = tid; a < m; a += nt) {
+            const int ia = act[a];
+            hv[a] = Tm[(size_t)q * LD + ia];
+            X[(size_t)ia * C + step] = (float)xs[a] / (float)nrm[ia];
+        }
+        if (tid == 0) {
+            residual[step] = (float)sqrt(r2 > 0.0 ? r2 : 0.0);
+            order[step] = q;
+        }
+        __syncthreads();
+        const double inv_d = 1.0 / d;
+        const float inv_m = 1.0f / (float)m;
+        for (int idx = tid; idx < m * m; idx += nt) {
+            const int a = (int)(((float)idx + 0.5f) * inv_m), b2 = idx - a * m;
+            double* e = Tm + (size_t)act[a] * LD + act[b2];
+            *e = fma(-hv[a] * inv_d, hv[b2], *e);
+        }
+        ArgBest b;
+        b.v = INFINITY; b.i = 0x7fffffff;
+        for (int a = tid; a < m; a += nt) {
+            if (a == aq) continue;
+            const int an = a - (a > aq ? 1 : 0);
+            const double xv = fma(-hv[a] * inv_d, xq, xs[a]);
+            xn[an] = xv;
+            actn[an] = act[a];
+            const float v = fabsf((float)xv);
+            if (v < b.v || (v == b.v && an < b.i)) { b.v = v; b.i = an; }
+        }
+        b = warp_argmin(b);
+        r2 = fma(-xq * inv_d, xq, r2);
+        if (lane == 0) { pv[warp] = b.v; pi[warp] = b.i; }
+        { double* tx = xs; xs = xn; xn = tx; }
+        { int* ta = act; act = actn; actn = ta; }
+        --m;
+        __syncthreads();
+    }
+
+    // ---- Rank_Candidate_Solutions (Extraction.py:505-572): relative jump, ascending selection sort carrying the
+    //      indices (swap with the first strict minimum of the tail), one warp, arg-min by shuffles ----
+    if (tid == 0) residual[C] = (float)sqrt(bb > 0.0 ? bb : 0.0);
+    __syncthreads();
+    for (int i = tid; i < C; i += nt) {
+        change[i] = (residual[i + 1] - residual[i]) / residual[i];
+        rank[i] = i;
+    }
+    __syncthreads();
+    if (warp == 0) {
         for (int i = 0; i < C; ++i) {
-            int k = i;
-            for (int j = i; j < C; ++j)
-                if (change[j] < change[k]) k = j;
-            const float tc = change[i]; change[i] = change[k]; change[k] = tc;
-            const int tr = rank[i]; rank[i] = rank[k]; rank[k] = tr;
+            ArgBest b;
+            b.v = INFINITY; b.i = 0x7fffffff;
+            bool any = false;
+            for (int j = i + lane; j < C; j += 32) {
+                const float v = change[j];
+                if (!any || v < b.v) { b.v = v; b.i = j; any = true; }
+            }
+            if (!any) { b.v = INFINITY; b.i = 0x7fffffff; }
+            b = warp_argmin(b);
+            if (lane == 0 && b.i < C && b.i != i && change[b.i] < change[i]) {
+                const float tc = change[i]; change[i] = change[b.i]; change[b.i] = tc;
+                const int tr = rank[i]; rank[i] = rank[b.i]; rank[b.i] = tr;
+            }
+            __syncwarp();
         }
     }
 }
 
-static size_t rfe_small_bytes(int C) { return sizeof(double) * (4 * (size_t)C + 1) + sizeof(int) * 2 * (size_t)C + 64; }
-static size_t rfe_matrix_bytes(int C) { return sizeof(double) * (size_t)(C + 1) * ((C + 1) | 1); }
+static size_t rfe_small_bytes(int C) {
+    return sizeof(double) * (5 * (size_t)C + 1) + sizeof(int) * 3 * (size_t)C + 64 * sizeof(float) + 64;
+}
+static size_t rfe_matrix_bytes(int C) { return sizeof(double) * (size_t)(C + 1) * (C + 1); }
 
 }  // namespace pdr
 
@@ -406,6 +598,7 @@ int pderead_library_dense(const float* d_dxn, int64_t M, int n, int K, float* d_
     if (rc) return rc;
     if (M < 0 || (M > 0 && (!d_dxn || !d_library))) return PDEREAD_ERR_BAD_ARGUMENT;
     if (M == 0) return PDEREAD_OK;
+    { const int rc_ = check_device(); if (rc_ != PDEREAD_OK) return rc_; }
     const size_t smem = sizeof(float) * ((size_t)(t.n + 1) * GP + GP + (size_t)t.C * GP);
     { const int rc_ = ensure_dynamic_smem((const void*)library_dense_kernel, smem); if (rc_ != PDEREAD_OK) return rc_; }
     const long long tiles = (M + GP - 1) / GP;
@@ -440,6 +633,7 @@ int pderead_rfe_gram(const double* d_G, const double* d_Atb, const double* d_btb
                      int32_t* d_order, int32_t* d_rank, float* d_change, void* ws, size_t ws_bytes, void* stream) {
     if (C < 1 || C > MAXC || !d_G || !d_Atb || !d_btb || !d_X || !d_residual || !d_order || !d_rank || !d_change)
         return PDEREAD_ERR_BAD_ARGUMENT;
+    { const int rc_ = check_device(); if (rc_ != PDEREAD_OK) return rc_; }
     int dev = 0, maxsm = 0;
     PDR_CUDA_CHECK(cudaGetDevice(&dev));
     PDR_CUDA_CHECK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -448,7 +642,10 @@ int pderead_rfe_gram(const double* d_G, const double* d_Atb, const double* d_btb
     if (!use_smem && (!ws || ws_bytes < mat)) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
     const size_t smem = use_smem ? small + mat : small;
     { const int rc_ = ensure_dynamic_smem((const void*)rfe_kernel, smem); if (rc_ != PDEREAD_OK) return rc_; }
-    rfe_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(d_G, d_Atb, d_btb, C, d_X, d_residual, d_order, d_rank, d_change,
+    int threads = (((C + 1) * (C + 1) / 8) + 31) & ~31;     // ~8 matrix entries per thread and step
+    if (threads < 128) threads = 128;
+    if (threads > 1024) threads = 1024;
+    rfe_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(d_G, d_Atb, d_btb, C, d_X, d_residual, d_order, d_rank, d_change,
                                                         (double*)ws, use_smem);
     PDR_CUDA_CHECK(cudaGetLastError());
     stage_mark((cudaStream_t)stream);

@@ -210,6 +210,7 @@ void set_last_cuda_error(cudaError_t e, const char* file, int line);
 // kernel serves several network shapes from several threads (autograd runs reverse calls on its own): this
 // only ever raises it, so a shape seen earlier can always be launched again.
 int ensure_dynamic_smem(const void* kernel, size_t smem);
+int check_device();                // PDEREAD_OK on compute capability 10.x, else PDEREAD_ERR_NOT_BLACKWELL
 void stage_mark(cudaStream_t s);   // measurement hook, see pderead_debug_stage_events
 
 // extraction.cu

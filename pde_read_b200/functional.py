@@ -358,7 +358,7 @@ def collocation_loss_grad(sol_spec, sol_tensors, pde_spec, pde_tensors, m: int, 
     coords = _check_tensor(coords.detach(), "Coords")
     M = coords.shape[0]
     if M_total is None:
-        M_total = M
+        M_total = M                     # (0 = gradients of the unscaled sum(R^2): the sharded path)
     with torch.cuda.device(coords.device):
         su, k1 = _fill_net(sol_spec, sol_tensors)
         sn, k2 = _fill_net(pde_spec, pde_tensors)
@@ -512,7 +512,11 @@ class ResidualFn(torch.autograd.Function):
 
 class CollocationLossFn(torch.autograd.Function):
     """mean(R^2) with the parameter gradients computed in the same fused pass (the loss is a
-    scalar, so the reverse pass can run eagerly and backward() only scales by the incoming grad)."""
+    scalar, so the reverse pass can run eagerly and backward() only scales by the incoming grad).
+
+    With a reducer (points sharded over ranks) every rank computes the gradient of its unscaled sum(R^2), the
+    global point count comes back with the all-reduce, and backward() applies 1 / count on the device: no
+    rank-local decision, no host synchronisation."""
 
     @staticmethod
     def forward(ctx, coords, sol_spec, pde_spec, m, n, n_sol, reducer, *tensors):
@@ -520,30 +524,43 @@ class CollocationLossFn(torch.autograd.Function):
         M = coords.shape[0]
         # (grad mode is always off inside Function.forward; needs_input_grad is the real signal)
         need_grad = any(ctx.needs_input_grad[7:])
-        M_total = reducer.total_points(M) if reducer is not None else M
+        M_total = 0 if reducer is not None else M          # 0: unscaled sums (C ABI)
+        factor = None
         if need_grad:
             step = collocation_loss_grad_graphed if (USE_CUDA_GRAPHS and M > 0) else collocation_loss_grad
             ss, flat, vu, vn, _ = step(sol_spec, sol_t, pde_spec, pde_t, m, n, coords,
-                                       M_total=M_total, extra_tail=4 if reducer is not None else 0)
+                                       M_total=M_total, extra_tail=reducer.TAIL if reducer is not None else 0)
             if reducer is not None:
-                ss = reducer.reduce(flat, ss)
-            ctx.save_for_backward(flat)
+                red = reducer.reduce(flat, ss, M)
+                loss = (red[0] / red[1]).to(torch.float32).reshape(())
+                factor = red[2].to(torch.float32)
+                ctx.save_for_backward(flat, factor)
+            else:
+                loss = (ss / float(M_total)).to(torch.float32).reshape(())
+                ctx.save_for_backward(flat)
             ctx.shapes = [tuple(t.shape) for t in tensors]
         else:
             _, ss = residual_forward(sol_spec, sol_t, pde_spec, pde_t, m, n, coords, want_resid=False)
             if reducer is not None:
-                ss = reducer.reduce(None, ss)
+                red = reducer.reduce(None, ss, M)
+                loss = (red[0] / red[1]).to(torch.float32).reshape(())
+            else:
+                loss = (ss / float(max(M_total, 1))).to(torch.float32).reshape(())
         ctx.need_grad = need_grad
+        ctx.has_factor = factor is not None
         ctx.flags = list(ctx.needs_input_grad[7:])
-        loss = (ss / float(M_total)).to(torch.float32).reshape(())
         return loss
 
     @staticmethod
     def backward(ctx, g):
         if not ctx.need_grad:
             return (None,) * (7 + len(ctx.flags))
-        (flat,) = ctx.saved_tensors
-        scaled = flat * g          # one launch for all parameter tensors
+        if ctx.has_factor:
+            flat, factor = ctx.saved_tensors
+            scaled = flat * (g * factor)
+        else:
+            (flat,) = ctx.saved_tensors
+            scaled = flat * g          # one launch for all parameter tensors
         grads, off = [], 0
         for shape, f in zip(ctx.shapes, ctx.flags):
             numel = 1

@@ -37,7 +37,14 @@ def shard_points(coords: torch.Tensor, rank: int, world_size: int) -> torch.Tens
 
 class ShardReducer:
     """All-reduce helper handed to Collocation_Loss (via Loss_Functions.set_reducer) and to
-    Extraction.Extract_PDE."""
+    Extraction.Extract_PDE.
+
+    No rank ever decides locally whether a collective happens: every call below issues exactly the same
+    sequence of all-reduces on every rank, and the global point count is never cached -- it travels with the
+    data.  A rank computes the gradient of its UNSCALED sum(R^2) (``M_total = 0`` in the C ABI); the point count
+    comes back in the tail of the same all-reduce and the 1 / count of the mean is applied on the device."""
+
+    TAIL = 4      # floats at the end of the packed gradient buffer: sum(R^2) hi, lo | count >> 12, count & 4095
 
     def __init__(self, group: Optional[dist.ProcessGroup] = None):
         if not dist.is_initialized():
@@ -45,19 +52,13 @@ class ShardReducer:
         self.group = group
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self._totals = {}
 
     def total_points(self, local_points: int) -> int:
-        """Sum of the ranks' local point counts (cached per local count: a training run keeps its
-        shard size, so this costs one tiny all-reduce once)."""
-        key = int(local_points)
-        if key not in self._totals:
-            t = torch.tensor([key], dtype=torch.int64)
-            dev = self._device()
-            t = t.to(dev)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-            self._totals[key] = int(t.item())
-        return self._totals[key]
+        """Sum of the ranks' local point counts.  Always a collective (every rank must call it); returns a
+        host integer, so it synchronises -- the training path uses reduce() instead."""
+        t = torch.tensor([int(local_points)], dtype=torch.int64, device=self._device())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return int(t.item())
 
     def _device(self) -> torch.device:
         backend = dist.get_backend(self.group)
@@ -65,21 +66,42 @@ class ShardReducer:
             return torch.device("cuda", torch.cuda.current_device())
         return torch.device("cpu")
 
-    def reduce(self, flat: Optional[torch.Tensor], sum_sq: torch.Tensor) -> torch.Tensor:
-        """Sum `flat` (float32 gradients with >= 2 spare floats at the end) and the float64 scalar
-        `sum_sq` over the ranks in one all-reduce; returns the global sum_sq (float64, shape [1]).
-        The scalar rides in the tail as a (hi, lo) float pair, which keeps ~48 bits of it."""
+    def reduce(self, flat: Optional[torch.Tensor], sum_sq: torch.Tensor, local_points: int) -> torch.Tensor:
+        """Sum `flat` (float32 gradients of the unscaled sum(R^2), with TAIL spare floats at the end) and the
+        float64 scalar `sum_sq` over the ranks in ONE all-reduce.  Returns a float64 tensor [3] on the device of
+        `sum_sq`: (global sum(R^2), global point count, 1 / global count).  With ``flat is None``
+        (forward-only) a float64 pair is reduced instead."""
+        M_as = 1
         if flat is None:
-            buf = sum_sq.to(torch.float64).reshape(1).clone()
+            buf = torch.cat([sum_sq.to(torch.float64).reshape(1),
+                             torch.tensor([float(local_points)], dtype=torch.float64, device=sum_sq.device)])
             dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
-            return buf
+            return torch.cat([buf, (float(M_as) / buf[1:2])])
+        tail = flat[-self.TAIL:]
+        out = torch.empty(3, dtype=torch.float64, device=flat.device)
+        if flat.is_cuda:
+            from . import _lib
+            lib = _lib.load()
+            stream = torch.cuda.current_stream(flat.device).cuda_stream
+            ss = sum_sq if (sum_sq.dtype == torch.float64 and sum_sq.is_cuda) else sum_sq.to(flat.device, torch.float64)
+            _lib.check(lib.pderead_loss_tail_pack(ss.data_ptr(), int(local_points), tail.data_ptr(), stream),
+                       "pderead_loss_tail_pack")
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            _lib.check(lib.pderead_loss_tail_unpack(tail.data_ptr(), M_as, out.data_ptr(), stream),
+                       "pderead_loss_tail_unpack")
+            return out
+        # CPU tensors (gloo tests of this logic): the same packing with torch ops
         ss = sum_sq.to(torch.float64).reshape(1)
         hi = ss.to(torch.float32)
-        lo = (ss - hi.to(torch.float64)).to(torch.float32)
-        flat[-2:-1] = hi
-        flat[-1:] = lo
+        tail[0:1] = hi
+        tail[1:2] = (ss - hi.to(torch.float64)).to(torch.float32)
+        tail[2] = float(int(local_points) >> 12)
+        tail[3] = float(int(local_points) & 4095)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-        return flat[-2:-1].to(torch.float64) + flat[-1:].to(torch.float64)
+        out[0] = tail[0].double() + tail[1].double()
+        out[1] = tail[2].double() * 4096.0 + tail[3].double()
+        out[2] = float(M_as) / out[1]
+        return out
 
     def reduce_gram(self, G: torch.Tensor, Atb: torch.Tensor, btb: torch.Tensor):
         C = G.shape[0]
@@ -87,17 +109,23 @@ class ShardReducer:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
         return buf[:C * C].view(C, C), buf[C * C:C * C + C], buf[C * C + C:]
 
+    def reduce_moments(self, moments: torch.Tensor) -> torch.Tensor:
+        """Sum a small float64 vector (count, sums and sums of squares of the batch statistics of a
+        Batch_Norm=True PDE network, Network.py:100-104) over the ranks."""
+        dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=self.group)
+        return moments
+
 
 def sharded_loss_and_grads(local_fn: Callable[[torch.Tensor, int], Tuple[torch.Tensor, torch.Tensor]],
                            coords: torch.Tensor, reducer: ShardReducer) -> Tuple[float, torch.Tensor]:
     """Reference semantics of a sharded collocation step, independent of where the arithmetic runs.
 
-    `local_fn(shard, M_total)` returns (sum of R^2 over the shard as float64[1], flat float32
-    gradient of sum(R^2)/M_total with >= 2 spare floats at the end).  On GPUs `local_fn` is the fused
-    CUDA call; the CPU tests inject the oracle.  Returns (global mean(R^2), reduced flat gradient).
+    `local_fn(shard)` returns (sum of R^2 over the shard as float64[1], flat float32 gradient of that
+    unscaled sum with ShardReducer.TAIL spare floats at the end).  On GPUs `local_fn` is the fused CUDA call;
+    the CPU tests inject the oracle.  Returns (global mean(R^2), reduced flat gradient of the global mean).
     """
     shard = shard_points(coords, reducer.rank, reducer.world_size)
-    M_total = coords.shape[0]
-    ss, flat = local_fn(shard, M_total)
-    ss = reducer.reduce(flat, ss)
-    return float(ss.item()) / float(M_total), flat
+    ss, flat = local_fn(shard)
+    out = reducer.reduce(flat, ss, shard.shape[0])
+    flat[:-ShardReducer.TAIL] *= out[2].to(torch.float32)
+    return float(out[0].item()) / float(out[1].item()), flat

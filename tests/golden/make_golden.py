@@ -197,8 +197,43 @@ def golden_library_small():
         np.savez_compressed(os.path.join(HERE, "library_n%d_k%d.npz" % (n, K)), **out)
 
 
+def golden_extract_k5():
+    """BASELINE config 5 shape at a size the reference finishes in seconds: shipped checkpoint, random.seed(0),
+    20 000 extraction points, K = 5 (C = 56) through the unmodified Extraction.py:178-572."""
+    U, N = load_ckpt_nets()
+    d = np.load(os.path.join(REF, "Data", "DataSets", "Burgers_Sine_N50_P5000.npz"))
+    random.seed(0)
+    bounds = d["Input_Bounds"].astype(np.float64)
+    E = Points.Generate_Points(bounds, 20000, torch.float32, torch.device('cpu'))
+    b, Lib, counts, mil = Extraction.Generate_Library(U, N, 1, 2, E, 5)
+    X, Res = Extraction.Recursive_Feature_Elimination(Lib, b)
+    Xr, Rr, chg = Extraction.Rank_Candidate_Solutions(X, Res)
+    C = Lib.shape[1]
+    order = []
+    for j in range(C):
+        sup = set(np.flatnonzero(X[:, j]).tolist())
+        nxt = set(np.flatnonzero(X[:, j + 1]).tolist()) if j + 1 < C else set()
+        gone = sorted(sup - nxt)
+        order.append(gone[0] if len(gone) == 1 else -1)
+    # margin of every elimination: (second smallest - smallest) / smallest |x| among the remaining features,
+    # in the unit-norm scaling RFE compares in (Extraction.py:467-476) -- lets the tests skip near-ties
+    norms = np.sqrt((Lib.astype(np.float64) ** 2).sum(axis=0))
+    margin = np.zeros(C)
+    for j in range(C):
+        xs = np.sort(np.abs(X[:, j].astype(np.float64) * norms)[np.flatnonzero(X[:, j])])
+        margin[j] = (xs[1] - xs[0]) / xs[0] if xs.size > 1 and xs[0] > 0 else np.inf
+    np.savez_compressed(os.path.join(HERE, "burgers_extract_k5.npz"),
+                        coords_head=E[:256].detach().numpy(), b_head=b[:256], lib_head=Lib[:256],
+                        counts=counts, X=X, Residual=Res, order=np.asarray(order, dtype=np.int64),
+                        margin=margin, X_Ranked=Xr, Residual_Ranked=Rr, Residual_Change=chg)
+    print("extract k5: order", order)
+    print("Residual", Res)
+    print("margins", np.round(margin, 4))
+
+
 if __name__ == "__main__":
     golden_checkpoint()
     golden_random()
     golden_library_small()
+    golden_extract_k5()
     print("done")

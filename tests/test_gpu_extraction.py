@@ -155,3 +155,128 @@ def test_generate_points_in_bounds_and_reproducible():
         col = P1[:, j].double()
         assert abs(col.mean().item() - (lo + hi) / 2) < 0.02 * (hi - lo)
         assert abs(col.var().item() - (hi - lo) ** 2 / 12) < 0.02 * (hi - lo) ** 2
+
+
+def _orders_from_supports(X):
+    C = X.shape[0]
+    out = []
+    for j in range(C):
+        sup = set(np.flatnonzero(X[:, j]).tolist())
+        nxt = set(np.flatnonzero(X[:, j + 1]).tolist()) if j + 1 < C else set()
+        gone = sorted(sup - nxt)
+        out.append(gone[0] if len(gone) == 1 else -1)
+    return out
+
+
+def test_extraction_golden_k5_c56(capsys):
+    """BASELINE config 5 at a size the reference finishes: shipped checkpoint, random.seed(0), 20000 points,
+    K = 5 -> C = 56 (tests/golden/burgers_extract_k5.npz, written by the unmodified reference,
+    Extraction.py:178-572).  All 56 eliminations, the residuals, the ranked top 5 and the printed #1 PDE,
+    through the reference-shaped calls (Generate_Library + Recursive_Feature_Elimination(A, b)) and through
+    the fused Extract_PDE."""
+    from pde_read_b200.Extraction import (Extract_PDE, Generate_Library, Print_Extracted_PDE, Rank_Candidate_Solutions,
+                                          Recursive_Feature_Elimination)
+    ck, z = load_golden("burgers_ckpt.npz"), load_golden("burgers_extract_k5.npz")
+    bounds = load_golden("burgers_data_loss.npz")["bounds"]
+    U = make_net(split_state(ck, "sol."), "Rational", 2)
+    N = make_net(split_state(ck, "pde."), "Rational", 3)
+    random.seed(0)
+    E = orc.generate_points(bounds, 20000)
+    assert np.array_equal(E[:256].numpy(), z["coords_head"])
+    C = 56
+    b, Lib, counts, mil = Generate_Library(U, N, 1, 2, E.to(DEV), 5, DEV)
+    assert Lib.shape == (20000, C) and list(counts) == list(z["counts"])
+    assert rel_err(b[:256], z["b_head"]) < 1e-5
+    for c in range(C):
+        assert rel_err(Lib[:256, c], z["lib_head"][:, c]) < 5e-5, c
+    X, Res = Recursive_Feature_Elimination(Lib, b)
+    Xr, Rr, chg = Rank_Candidate_Solutions(X, Res)
+    fX, fRes, fXr, fRr, fchg, fcounts, fmil, order = Extract_PDE(U, N, 1, 2, E.to(DEV), 5)
+    want_order = [int(v) for v in z["order"]]
+    margin = z["margin"]
+    for got_X, got_Res, got_Xr, got_Rr in ((X, Res, Xr, Rr), (fX, fRes, fXr, fRr)):
+        # the reference sums its float32 residuals sequentially (Extraction.py:479-483): 2e-4 covers its own rounding
+        np.testing.assert_allclose(got_Res, z["Residual"], rtol=2e-4)
+        got_order = _orders_from_supports(got_X)
+        # identical elimination order; a step may only differ where the reference's own margin between the two
+        # smallest |x| is a near-tie (< 1 %): there are none below 0.9 % in this fixture, so demand equality
+        assert got_order == want_order, [(j, a, w, float(margin[j])) for j, (a, w) in enumerate(zip(got_order, want_order)) if a != w]
+        assert rel_err(got_X, z["X"]) < 1e-3
+        np.testing.assert_allclose(got_Rr, z["Residual_Ranked"], rtol=2e-4)
+        for j in range(C - 5, C):
+            assert set(np.flatnonzero(got_Xr[:, j]).tolist()) == set(np.flatnonzero(z["X_Ranked"][:, j]).tolist())
+            np.testing.assert_allclose(got_Xr[:, j], z["X_Ranked"][:, j], rtol=1e-4, atol=1e-6)
+    assert [int(v) for v in order] == want_order
+    # with the degree-5 library columns 3 and 5 are still D_x^2 U and U D_x U
+    best = fXr[:, -1]
+    assert set(np.flatnonzero(best).tolist()) == {3, 5}
+    assert abs(best[3] - 0.076364) < 1e-4 * 0.076364 + 2e-6 and abs(best[5] + 0.747831) < 1e-4 * 0.747831
+    Print_Extracted_PDE(best, 1, fcounts, fmil)
+    out = capsys.readouterr().out
+    assert "0.076364(D_x^2 U)" in out and "-0.747831(U)(D_x U)" in out
+
+
+def test_rfe_c252_global_memory_branch_matches_oracle():
+    """n = 4, K = 5 -> C = 252 (the C5 stress shape): the (C+1)^2 float64 system does not fit shared memory, so
+    rfe_kernel keeps it in the caller's workspace (use_smem = 0).  Random-init 5x100 Rational nets, 3000 points;
+    cond(scaled Gram) ~ 3e9.  Oracle = reference-faithful RFE (numpy lstsq on the tall float32 library)."""
+    from pde_read_b200.Extraction import Extract_PDE, Generate_Library, Recursive_Feature_Elimination
+    n, K, M = 4, 5, 3000
+    su = orc.init_network(5, 100, 2, "Rational", seed=11)
+    sn = orc.init_network(5, 100, n + 1, "Rational", seed=12)
+    U, N = make_net(su, "Rational", 2), make_net(sn, "Rational", n + 1)
+    P = torch.rand(M, 2, generator=torch.Generator().manual_seed(3)) * torch.tensor([5.0, 9.96]) + torch.tensor([0.0, -5.0])
+    b_o, Lib_o, _, _ = orc.generate_library(su, "Rational", sn, "Rational", 1, n, P, K)
+    Xo, Reso, order_o = orc.recursive_feature_elimination(Lib_o, b_o)
+    C = Lib_o.shape[1]
+    assert C == 252
+    # (a) the solver alone, on the oracle's own library: identical elimination order
+    X, Res = Recursive_Feature_Elimination(Lib_o, b_o)
+    assert _orders_from_supports(X) == order_o
+    np.testing.assert_allclose(Res, Reso, rtol=1e-4)
+    assert rel_err(X, Xo) < 1e-3
+    # (b) the whole fused pipeline (4th-order jets at 5e-5 perturb the near-ties of the first eliminations: compare
+    #     residuals everywhere, and the order over the last 40 steps, where the margins are wide)
+    fX, fRes, fXr, fRr, fchg, fcounts, fmil, order = Extract_PDE(U, N, 1, n, P.to(DEV), K)
+    np.testing.assert_allclose(fRes, Reso, rtol=2e-3)
+    assert [int(v) for v in order[-40:]] == order_o[-40:]
+    assert sorted(int(v) for v in order) == list(range(C))
+
+
+def test_rfe_rank_deficient_library_states_its_semantics():
+    """numpy.linalg.lstsq (Extraction.py:464) returns the minimum-norm solution for a rank-deficient library; the
+    Gram solver cannot see a dependent column (its pivot is ~0), keeps its coefficient at 0 and eliminates it FIRST,
+    after which every step equals the reference's steps on the library without that column.  A zero column behaves
+    the same way (the reference divides by its zero norm and returns NaN)."""
+    from pde_read_b200.Extraction import Recursive_Feature_Elimination
+    rng = np.random.default_rng(1)
+    M, C = 3000, 14
+    A = rng.normal(size=(M, C)).astype(np.float32)
+    x_true = np.zeros(C, dtype=np.float32)
+    x_true[[2, 5, 9]] = [1.5, -2.0, 0.7]
+    b = (A @ x_true + 0.1 * rng.normal(size=M)).astype(np.float32)
+    A[:, 11] = A[:, 5]                    # duplicate of an important column
+    X, Res = Recursive_Feature_Elimination(A, b)
+    assert np.all(np.isfinite(X)) and np.all(np.isfinite(Res))
+    order = _orders_from_supports(X)
+    # the later twin never enters the fit
+    assert np.all(X[11, :] == 0)
+    keep = [c for c in range(C) if c != 11]
+    Xk, Resk, order_k = orc.recursive_feature_elimination(A[:, keep], b)
+    np.testing.assert_allclose(Res[1:], Resk, rtol=1e-4)
+    assert Res[0] == Res[1]
+    assert rel_err(X[keep][:, 1:], Xk) < 1e-4
+    # what the reference does instead: both twins carry half the coefficient until one of them is the smallest entry
+    Xo, Reso, order_o = orc.recursive_feature_elimination(A, b)
+    assert abs(Xo[5, 0] - Xo[11, 0]) < 1e-3 * abs(Xo[5, 0]) and abs(Xo[5, 0] + Xo[11, 0] - Xk[5, 0]) < 1e-3 * abs(Xk[5, 0])
+    np.testing.assert_allclose(Res[0], Reso[0], rtol=1e-4)          # same fit, different split
+    # the final candidates (one twin gone in both) agree again
+    np.testing.assert_allclose(Res[-3:], Reso[-3:], rtol=1e-4)
+    # zero column
+    A2 = A[:, keep].copy()
+    A2[:, 3] = 0
+    X2, Res2 = Recursive_Feature_Elimination(A2, b)
+    assert np.all(np.isfinite(X2)) and np.all(X2[3, :] == 0)
+    keep2 = [c for c in range(A2.shape[1]) if c != 3]
+    X2k, Res2k, _ = orc.recursive_feature_elimination(A2[:, keep2], b)
+    np.testing.assert_allclose(Res2[1:], Res2k, rtol=1e-4)

@@ -46,9 +46,9 @@ def _worker(rank, world, port, q):
         assert red.world_size == world and red.rank == rank
         assert red.total_points(shard_points(P, rank, world).shape[0]) == P.shape[0]
 
-        def local_fn(shard, M_total):
-            loss, gs, gp = orc.collocation_loss_and_grads(sol, "Tanh", pde, "Tanh", 1, 2, shard, total_points=M_total)
-            return torch.tensor([loss * M_total], dtype=torch.float64), _flat(gs, gp)
+        def local_fn(shard):
+            loss, gs, gp = orc.collocation_loss_and_grads(sol, "Tanh", pde, "Tanh", 1, 2, shard, total_points=1)
+            return torch.tensor([loss], dtype=torch.float64), _flat(gs, gp)
 
         loss, flat = sharded_loss_and_grads(local_fn, P, red)
         # Gram all-reduce
@@ -89,3 +89,59 @@ def test_two_rank_sharded_step_matches_single_process():
         assert abs(btb - float((b.astype(np.float64) ** 2).sum())) < 1e-10
     # both ranks end with bit-identical reduced buffers (so they take identical optimizer steps)
     assert np.array_equal(results[0][2], results[1][2])
+
+
+def _worker_totals(rank, world, port, q):
+    """Two point sets whose totals differ (95 and 94) while rank 1's shard size is the same (47): the advisor's
+    stale-total scenario.  Every rank must still issue the same collectives and divide by the right count."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pde_read_b200.parallel import ShardReducer, shard_points, sharded_loss_and_grads
+        torch.set_num_threads(2)
+        z = load_golden("random_tanh_m1n2.npz")
+        sol, pde = split_state(z, "sol."), split_state(z, "pde.")
+        P = torch.from_numpy(z["coords"])
+        red = ShardReducer()
+
+        def local_fn(shard):
+            loss, gs, gp = orc.collocation_loss_and_grads(sol, "Tanh", pde, "Tanh", 1, 2, shard, total_points=1)
+            return torch.tensor([loss], dtype=torch.float64), _flat(gs, gp)
+
+        out = []
+        for M in (95, 94, 95):
+            sizes = shard_points(P[:M], rank, world).shape[0]
+            loss, flat = sharded_loss_and_grads(local_fn, P[:M], red)
+            out.append((M, sizes, loss, flat[:-4].numpy().copy(), red.total_points(sizes)))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_totals_follow_the_data_not_a_cache():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_totals, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    z = load_golden("random_tanh_m1n2.npz")
+    sol, pde = split_state(z, "sol."), split_state(z, "pde.")
+    P = torch.from_numpy(z["coords"])
+    assert [o[1] for o in results[1]] == [47, 47, 47]          # same shard size on rank 1 for both totals
+    assert [o[1] for o in results[0]] == [48, 47, 48]
+    for M_idx, M in enumerate((95, 94, 95)):
+        loss1, gs, gp = orc.collocation_loss_and_grads(sol, "Tanh", pde, "Tanh", 1, 2, P[:M])
+        flat1 = _flat(gs, gp, tail=0).numpy()
+        for rank in (0, 1):
+            m_, _, loss, flat, total = results[rank][M_idx]
+            assert total == M
+            assert abs(loss - loss1) <= 1e-6 * abs(loss1), (rank, M)
+            assert rel_err(flat, flat1) < 2e-5, (rank, M)
