@@ -200,6 +200,10 @@ int pderead_fma_peak_probe(int variant, int iters, float* d_sink, double* h_flop
  * without synchronising.  pderead_debug_stage_events_recorded() returns how many were recorded. */
 int pderead_debug_stage_events(void* const* events, int count);
 int pderead_debug_stage_events_recorded(void);
+/* What each recorded event followed: 0 other, 1 weight packing, 2 jet forward (U), 3 plain-MLP forward (N),
+ * 4 plain-MLP reverse, 5 jet reverse, 6 partial-gradient reduction, 7 library + Gram, 8 RFE + ranking,
+ * 9 optimiser step, 10 input-normalisation helpers.  Fills h_tags[0..return value). */
+int pderead_debug_stage_tags(int32_t* h_tags, int capacity);
 /* Tensor-core policy for the hidden-layer products (tcgen05, 3xTF32; widths 8..128, depth >= 2):
  *   0 off   - CUDA-core kernels everywhere;
  *   1 auto  - default: forward-only calls of networks wider than 64 (>= 3 hidden layers) use the tensor cores, the gradient

@@ -91,6 +91,7 @@ PROTOTYPES = {
     "pderead_fma_peak_probe": (c_int, [c_int, c_int, c_void_p, POINTER(c_double), c_void_p]),
     "pderead_debug_stage_events": (c_int, [POINTER(c_void_p), c_int]),
     "pderead_debug_stage_events_recorded": (c_int, []),
+    "pderead_debug_stage_tags": (c_int, [POINTER(c_int32), c_int]),
     "pderead_debug_set_tensor_cores": (c_int, [c_int]),
 }
 

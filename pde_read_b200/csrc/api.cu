@@ -59,8 +59,13 @@ int ensure_dynamic_smem(const void* kernel, size_t smem) {
 
 static thread_local cudaEvent_t* g_stage_events = nullptr;
 static thread_local int g_stage_count = 0, g_stage_next = 0;
-void stage_mark(cudaStream_t s) {
-    if (g_stage_events && g_stage_next < g_stage_count) cudaEventRecord(g_stage_events[g_stage_next++], s);
+constexpr int MAX_STAGE_TAGS = 1024;
+static thread_local unsigned char g_stage_tags[MAX_STAGE_TAGS];
+void stage_mark(cudaStream_t s, int tag) {
+    if (g_stage_events && g_stage_next < g_stage_count) {
+        if (g_stage_next < MAX_STAGE_TAGS) g_stage_tags[g_stage_next] = (unsigned char)tag;
+        cudaEventRecord(g_stage_events[g_stage_next++], s);
+    }
 }
 
 // The kernels are built for sm_100a only: any other device gets PDEREAD_ERR_NOT_BLACKWELL instead of a launch
@@ -474,7 +479,7 @@ static int tc_pack(const NetDev& n, int mrows, int Kpad, int NB, int a_rs, int a
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
     tc_pack_weights_kernel<<<blocks, 256, 0, s>>>(n, mrows, Kpad, NB, a_rs, a_bytes, transpose, img);
     PDR_CUDA_CHECK(cudaGetLastError());
-    stage_mark(s);
+    stage_mark(s, ST_PACK);
     return PDEREAD_OK;
 }
 
@@ -594,12 +599,12 @@ static int dispatch_bwd_raw(int act, int nx, int nt, const BwdArgs& a, int grid,
 
 static int dispatch_fwd(int act, int nx, int nt, const FwdArgs& a, cudaStream_t s) {
     const int rc = dispatch_fwd_raw(act, nx, nt, a, s);
-    if (rc == PDEREAD_OK) stage_mark(s);
+    if (rc == PDEREAD_OK) stage_mark(s, (nx + nt) ? ST_FWD_JET : ST_FWD_PLAIN);
     return rc;
 }
 static int dispatch_bwd(int act, int nx, int nt, const BwdArgs& a, int grid, cudaStream_t s) {
     const int rc = dispatch_bwd_raw(act, nx, nt, a, grid, s);
-    if (rc == PDEREAD_OK) stage_mark(s);
+    if (rc == PDEREAD_OK) stage_mark(s, (nx + nt) ? ST_BWD_JET : ST_BWD_PLAIN);
     return rc;
 }
 
@@ -659,7 +664,7 @@ static int pack(const NetDev& n, float* wt, float* wn, cudaStream_t s) {
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
     pack_weights_kernel<<<blocks, 256, 0, s>>>(n, wt, wn);
     PDR_CUDA_CHECK(cudaGetLastError());
-    stage_mark(s);
+    stage_mark(s, ST_PACK);
     return PDEREAD_OK;
 }
 
@@ -668,7 +673,7 @@ static int reduce_partials(const float* gpart, int nparts, const GradLayout& lay
     const int blocks = (lay.total + 31) / 32;
     reduce_partials_kernel<<<blocks, 256, 0, s>>>(gpart, nparts, lay.total, tab, beta, scale);
     PDR_CUDA_CHECK(cudaGetLastError());
-    stage_mark(s);
+    stage_mark(s, ST_REDUCE);
     return PDEREAD_OK;
 }
 
@@ -677,9 +682,9 @@ static int dispatch_tc_fwd(int act, int nx, int nt, const TcFwdArgs& a, cudaStre
 #define CASE(X_, T_)                                                   \
     if (nx == X_ && nt == T_) {                                        \
         switch (act) {                                                 \
-            case 0: { const int rc = launch_tc_fwd<0, X_, T_>(a, s); if (rc == PDEREAD_OK) stage_mark(s); return rc; } \
-            case 1: { const int rc = launch_tc_fwd<1, X_, T_>(a, s); if (rc == PDEREAD_OK) stage_mark(s); return rc; } \
-            case 2: { const int rc = launch_tc_fwd<2, X_, T_>(a, s); if (rc == PDEREAD_OK) stage_mark(s); return rc; } \
+            case 0: { const int rc = launch_tc_fwd<0, X_, T_>(a, s); if (rc == PDEREAD_OK) stage_mark(s, (X_ + T_) ? ST_FWD_JET : ST_FWD_PLAIN); return rc; } \
+            case 1: { const int rc = launch_tc_fwd<1, X_, T_>(a, s); if (rc == PDEREAD_OK) stage_mark(s, (X_ + T_) ? ST_FWD_JET : ST_FWD_PLAIN); return rc; } \
+            case 2: { const int rc = launch_tc_fwd<2, X_, T_>(a, s); if (rc == PDEREAD_OK) stage_mark(s, (X_ + T_) ? ST_FWD_JET : ST_FWD_PLAIN); return rc; } \
         }                                                              \
     }
     PDR_FWD_COMBOS(CASE)
@@ -691,9 +696,9 @@ static int dispatch_tc_bwd(int act, int nx, int nt, const TcBwdArgs& a, int grid
 #define CASE(X_, T_)                                                   \
     if (nx == X_ && nt == T_) {                                        \
         switch (act) {                                                 \
-            case 0: { const int rc = launch_tc_bwd<0, X_, T_>(a, grid, s); if (rc == PDEREAD_OK) stage_mark(s); return rc; } \
-            case 1: { const int rc = launch_tc_bwd<1, X_, T_>(a, grid, s); if (rc == PDEREAD_OK) stage_mark(s); return rc; } \
-            case 2: { const int rc = launch_tc_bwd<2, X_, T_>(a, grid, s); if (rc == PDEREAD_OK) stage_mark(s); return rc; } \
+            case 0: { const int rc = launch_tc_bwd<0, X_, T_>(a, grid, s); if (rc == PDEREAD_OK) stage_mark(s, (X_ + T_) ? ST_BWD_JET : ST_BWD_PLAIN); return rc; } \
+            case 1: { const int rc = launch_tc_bwd<1, X_, T_>(a, grid, s); if (rc == PDEREAD_OK) stage_mark(s, (X_ + T_) ? ST_BWD_JET : ST_BWD_PLAIN); return rc; } \
+            case 2: { const int rc = launch_tc_bwd<2, X_, T_>(a, grid, s); if (rc == PDEREAD_OK) stage_mark(s, (X_ + T_) ? ST_BWD_JET : ST_BWD_PLAIN); return rc; } \
         }                                                              \
     }
     PDR_BWD_COMBOS(CASE)
@@ -789,6 +794,13 @@ int pderead_debug_stage_events(void* const* events, int count) {
     return PDEREAD_OK;
 }
 int pderead_debug_stage_events_recorded(void) { return g_stage_next; }
+int pderead_debug_stage_tags(int32_t* h_tags, int capacity) {
+    if (!h_tags || capacity < 0) return PDEREAD_ERR_BAD_ARGUMENT;
+    int n = g_stage_next < MAX_STAGE_TAGS ? g_stage_next : MAX_STAGE_TAGS;
+    if (n > capacity) n = capacity;
+    for (int i = 0; i < n; ++i) h_tags[i] = g_stage_tags[i];
+    return n;
+}
 
 int pderead_debug_set_tensor_cores(int mode) {
     (void)tc_mode();

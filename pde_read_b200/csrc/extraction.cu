@@ -302,7 +302,7 @@ int gram_launch(const LibTable& t, bool dense, const float* src, const float* b,
     }
 #undef PDR_GRAM_LAUNCH
     PDR_CUDA_CHECK(cudaGetLastError());
-    stage_mark(s);
+    stage_mark(s, ST_GRAM);
     return PDEREAD_OK;
 }
 
@@ -648,7 +648,7 @@ int pderead_rfe_gram(const double* d_G, const double* d_Atb, const double* d_btb
     rfe_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(d_G, d_Atb, d_btb, C, d_X, d_residual, d_order, d_rank, d_change,
                                                         (double*)ws, use_smem);
     PDR_CUDA_CHECK(cudaGetLastError());
-    stage_mark((cudaStream_t)stream);
+    stage_mark((cudaStream_t)stream, ST_RFE);
     return PDEREAD_OK;
 }
 

@@ -211,7 +211,11 @@ void set_last_cuda_error(cudaError_t e, const char* file, int line);
 // only ever raises it, so a shape seen earlier can always be launched again.
 int ensure_dynamic_smem(const void* kernel, size_t smem);
 int check_device();                // PDEREAD_OK on compute capability 10.x, else PDEREAD_ERR_NOT_BLACKWELL
-void stage_mark(cudaStream_t s);   // measurement hook, see pderead_debug_stage_events
+// measurement hook, see pderead_debug_stage_events / pderead_debug_stage_tags: records the next caller-owned event
+// after a launch, together with what was launched
+enum StageTag { ST_OTHER = 0, ST_PACK = 1, ST_FWD_JET = 2, ST_FWD_PLAIN = 3, ST_BWD_PLAIN = 4, ST_BWD_JET = 5,
+                ST_REDUCE = 6, ST_GRAM = 7, ST_RFE = 8, ST_OPTIM = 9, ST_BN = 10 };
+void stage_mark(cudaStream_t s, int tag = ST_OTHER);
 
 // extraction.cu
 int library_gram_launch(const float* dxn, const float* b, long long M, int n, int K, double* G, double* Atb,
