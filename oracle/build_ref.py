@@ -25,7 +25,7 @@ OUT = os.path.join(HERE, "_ref", "Code")
 def build(verbose: bool = False) -> bool:
     """Returns True when oracle/_ref/Code holds all modules (freshly built, or built earlier)."""
     if not os.path.isdir(REF_CODE):
-        return all(os.path.exists(os.path.join(OUT, m + ".pyc")) for m in MODULES)
+        return available()
     os.makedirs(OUT, exist_ok=True)
     for m in MODULES:
         src, dst = os.path.join(REF_CODE, m + ".py"), os.path.join(OUT, m + ".pyc")
@@ -33,6 +33,12 @@ def build(verbose: bool = False) -> bool:
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
         if verbose:
             print("compiled", src, "->", dst)
+    # the same compiled modules once more as one archive (zipimport reads .pyc members): a snapshot tool that
+    # drops *.pyc files then still carries the build
+    import zipfile
+    with zipfile.ZipFile(os.path.join(OUT, "reference_code.zip"), "w") as zf:
+        for m in MODULES:
+            zf.write(os.path.join(OUT, m + ".pyc"), m + ".pyc")
     with open(os.path.join(OUT, "PYTHON_VERSION"), "w") as fh:
         fh.write("%d.%d\n" % sys.version_info[:2])
     return True
@@ -44,15 +50,18 @@ def available() -> bool:
             ok = fh.read().strip() == "%d.%d" % sys.version_info[:2]
     except OSError:
         return False
-    return ok and all(os.path.exists(os.path.join(OUT, m + ".pyc")) for m in MODULES)
+    return ok and (all(os.path.exists(os.path.join(OUT, m + ".pyc")) for m in MODULES)
+                   or os.path.exists(os.path.join(OUT, "reference_code.zip")))
 
 
 def import_reference():
     """(Network, PDE_Residual, Loss_Functions, Extraction, Points) of the unmodified reference, or None."""
     if not available():
         return None
-    if OUT not in sys.path:
-        sys.path.insert(0, OUT)
+    loose = all(os.path.exists(os.path.join(OUT, m + ".pyc")) for m in MODULES)
+    entry = OUT if loose else os.path.join(OUT, "reference_code.zip")
+    if entry not in sys.path:
+        sys.path.insert(0, entry)
     import importlib
     return tuple(importlib.import_module(m) for m in MODULES)
 
