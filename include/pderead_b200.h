@@ -179,6 +179,45 @@ int pderead_rfe_gram(const double* d_G, const double* d_Atb, const double* d_btb
 int pderead_generate_points(const double* h_bounds, int dim, int64_t num_points, uint64_t seed,
                             uint64_t offset, float* d_points, void* stream);
 
+/* ---- input normalisation of the PDE network -------------------------------------------------
+ * reference Network.py:100-104,194-195: with "PDE Network - Normalize Inputs" the PDE network applies
+ * torch.nn.BatchNorm1d to its inputs [U, D_x U, ..]: the one operation of the path that couples the points.
+ * Two phases: (1) pderead_input_moments accumulates {count, sum_d, sum_d of squares} in float64 (the host sums the
+ * 1 + 2 din numbers over ranks when points are sharded); (2) pderead_bn_fold turns statistics + gamma/beta into
+ * folded first-layer parameters (the normalisation is affine in the inputs), after which the ordinary MLP entry
+ * points run on a pderead_net whose weight[0] / bias[0] point at the folded copies.  training != 0: batch statistics
+ * (biased variance), running statistics updated with `momentum` (unbiased variance) and *d_num_batches += 1, as
+ * BatchNorm1d does; training == 0: running statistics.  d_stats receives [mean (din) | rstd (din)].
+ * Reverse: pderead_mlp_backward on the folded network yields gW0', gb0' and the input gradient at fixed statistics;
+ * pderead_bn_grad_sums -> {sum_i gW0'[i][d] W0[i][d], sum_i gb0'[i] W0[i][d]} (sum these over ranks for the
+ * `global` argument); pderead_bn_backward rewrites gW0' -> gW0 in place (gb0 = gb0'), writes the gradients of
+ * gamma / beta (from the local sums) and the seeds a_d, b_d (from the global sums); pderead_bn_input_grad adds the
+ * batch-statistics term a_d + b_d x_pd to the input gradient. */
+int pderead_input_moments(const float* d_x, int64_t M, int din, double* d_moments, void* stream);
+int pderead_bn_fold(const pderead_net* net, const float* d_gamma, const float* d_beta, const double* d_moments,
+                    int training, float momentum, float eps, float* d_running_mean, float* d_running_var,
+                    int64_t* d_num_batches, float* d_w0_folded, float* d_b0_folded, float* d_stats, void* stream);
+int pderead_bn_grad_sums(const pderead_net* net, const float* d_gw0_folded, const float* d_gb0_folded, double* d_sums,
+                         void* stream);
+int pderead_bn_backward(const pderead_net* net, const float* d_gamma, const float* d_beta, const float* d_stats,
+                        const double* d_moments, const double* d_sums_local, const double* d_sums_global, int training,
+                        float* d_gw0, const float* d_gb0, float* d_ggamma, float* d_gbeta, float* d_seed_ab,
+                        void* stream);
+int pderead_bn_input_grad(float* d_gin, const float* d_x, int64_t M, int din, const float* d_seed_ab, void* stream);
+
+/* ---- optimiser step -------------------------------------------------------------------
+ * reference main.py:63-71 builds torch.optim.Adam / SGD(momentum 0.9, nesterov) over the ~50 parameter tensors
+ * of both networks and Test_Train.py:105 steps it.  Here all parameters, gradients and optimiser state live in
+ * flat float32 buffers of n elements with one common layout (every tensor 16-byte aligned, padding zero) and one
+ * launch updates them, in torch's operation order.  d_state2 = {step count (float), internal ticket (zero it
+ * once)}; the kernel advances the count itself, so the launch can sit inside a CUDA graph.  grad_scale multiplies
+ * the gradients first (1 for a plain step). */
+int pderead_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, float grad_scale, float* d_state2,
+                      void* stream);
+int pderead_sgd_step(float* d_params, const float* d_grads, float* d_momentum_buf, int64_t n, float lr, float momentum,
+                     int nesterov, float weight_decay, float grad_scale, float* d_state2, void* stream);
+
 /* ---- sharded points (one process per GPU): the cross-rank part of Collocation_Loss ----------------
  * mean(R^2) (reference Loss_Functions.py:65) and its gradient are sums over points, so every rank works on
  * its slice (pderead_collocation_loss_grad with M_total = 0: unscaled sums) and ONE float32 SUM all-reduce of

@@ -142,11 +142,13 @@ def Extract_PDE(
     float64 Gram system is all-reduced before the solves."""
     n, K = int(Spatial_Derivative_Order), int(Poly_Degree)
     if getattr(PDE_NN, "Batch_Norm", False):
-        # unfused: the input BatchNorm of N sits between the two kernels (statistics over all these points)
+        # two-phase: U-jets -> moments over all extraction points (summed over ranks when sharded) -> N with the
+        # input normalisation folded into its first layer
         su, tu = F.net_spec(Sol_NN), F.net_tensors(Sol_NN)
         _, Dxn_U = F.sol_derivatives_forward(su, tu, 0, n, Coords)
-        with torch.no_grad():
-            b = PDE_NN(Dxn_U).view(-1)
+        mom = F.input_moments(Dxn_U, reducer) if PDE_NN.training else None
+        fold = F.FoldedNet(PDE_NN, mom, PDE_NN.training)
+        b = F.mlp_forward(fold.spec, fold.tensors, Dxn_U)
         G, Atb, btb = F.library_gram(Dxn_U, b, n, K)
     else:
         su, sn = F.net_spec(Sol_NN), F.net_spec(PDE_NN)

@@ -33,10 +33,13 @@ def Collocation_Loss(
     m = max(int(Time_Derivative_Order), 1)
     n = int(Spatial_Derivative_Order)
     if getattr(PDE_NN, "Batch_Norm", False):
-        if _reducer is not None:
-            raise NotImplementedError("Batch_Norm=True with sharded points needs synchronised batch statistics")
+        # input normalisation couples the points: U-jets -> moments (all-reduced over ranks) -> N with the
+        # normalisation folded into its first layer; the reverse pass adds the batch-statistics terms to d/dDxn_U
         from .PDE_Residual import PDE_Residual
-        return (PDE_Residual(Sol_NN, PDE_NN, m, n, Collocation_Coords, Data_Type, Device) ** 2).mean()
+        R = PDE_Residual(Sol_NN, PDE_NN, m, n, Collocation_Coords, Data_Type, Device)
+        if _reducer is None:
+            return (R ** 2).mean()
+        return F.ShardedMeanSquareFn.apply(R, _reducer)
     su, sn = F.net_spec(Sol_NN), F.net_spec(PDE_NN)
     tu, tn = F.net_tensors(Sol_NN), F.net_tensors(PDE_NN)
     return F.CollocationLossFn.apply(Collocation_Coords, su, sn, m, n, len(tu), _reducer, *tu, *tn)

@@ -97,8 +97,13 @@ class Neural_Network(torch.nn.Module):
         CUDA MLP kernel; differentiable w.r.t. X and the parameters."""
         if self.Batch_Norm:
             # input normalisation (batch statistics in train mode, running statistics in eval mode, running
-            # statistics updated as a side effect): torch's own BatchNorm1d, exactly the reference's layer
-            X = self.Norm_Layer(X)
+            # statistics updated as a side effect).  Norm_Layer only HOLDS the parameters and buffers of the
+            # reference's BatchNorm1d (checkpoint layout); the arithmetic is the two-phase CUDA path: moments of the
+            # inputs (all-reduced when the points are sharded), normalisation folded into the first Linear layer
+            from . import Loss_Functions
+            bn = self.Norm_Layer
+            out = F.BNInputMLPFn.apply(X, self, Loss_Functions._reducer, bn.weight, bn.bias, *F.net_tensors(self))
+            return out.view(-1, 1)
         spec = F.net_spec(self, allow_input_norm=True)
         out = F.MLPFn.apply(X.contiguous(), spec, *F.net_tensors(self))
         return out.view(-1, 1)

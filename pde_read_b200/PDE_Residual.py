@@ -48,8 +48,9 @@ def PDE_Residual(
     m = max(int(Time_Derivative_Order), 1)
     n = int(Spatial_Derivative_Order)
     if getattr(PDE_NN, "Batch_Norm", False):
-        # "PDE Network - Normalize Inputs": batch statistics couple all points, so the residual is composed
-        # from the U-jet kernel, torch's BatchNorm1d and the MLP kernel instead of the fused call
+        # "PDE Network - Normalize Inputs": batch statistics couple all points, so the residual is composed from the
+        # U-jet kernel, the moments kernel and the MLP kernel on the network with the normalisation folded into its
+        # first layer (two-phase path, functional.BNInputMLPFn) instead of the single fused call
         Dtm_U, Dxn_U = Evaluate_Derivatives(Sol_NN, m, n, Coords, Data_Type, Device)
         return Dtm_U - PDE_NN(Dxn_U).view(-1)
     su, sn = F.net_spec(Sol_NN), F.net_spec(PDE_NN)

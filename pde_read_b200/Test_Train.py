@@ -28,13 +28,18 @@ def Discovery_Training(
     Sol_NN.train()
     PDE_NN.train()
     fast = _fast_closure_ok(Sol_NN, PDE_NN, Collocation_Coords, Data_Coords, Data_Values, Data_Type)
+    if fast and _graph_ok(Sol_NN, PDE_NN, Collocation_Coords, Optimizer):
+        # whole epoch (closure + optimiser step) as one CUDA-graph replay
+        _graphed_epoch(Sol_NN, PDE_NN, max(int(Time_Derivative_Order), 1), int(Spatial_Derivative_Order),
+                       Collocation_Coords, Data_Coords, Data_Values, Optimizer)
+        return
 
     def Discovery_Closure():
         if torch.is_grad_enabled():
             Optimizer.zero_grad()
         if fast and torch.is_grad_enabled():
             return _fused_closure(Sol_NN, PDE_NN, max(int(Time_Derivative_Order), 1), int(Spatial_Derivative_Order),
-                                  Collocation_Coords, Data_Coords, Data_Values)
+                                  Collocation_Coords, Data_Coords, Data_Values, Optimizer)
         Loss = (Collocation_Loss(Sol_NN, PDE_NN, Time_Derivative_Order, Spatial_Derivative_Order, Collocation_Coords,
                                  Data_Type, Device)
                 + Data_Loss(Sol_NN, Data_Coords, Data_Values, Data_Type, Device))
@@ -70,22 +75,101 @@ def _fast_closure_ok(Sol_NN, PDE_NN, Collocation_Coords, Data_Coords, Data_Value
     return all(p.requires_grad for p in list(Sol_NN.parameters()) + list(PDE_NN.parameters()))
 
 
-def _fused_closure(Sol_NN, PDE_NN, m, n, Collocation_Coords, Data_Coords, Data_Values) -> torch.Tensor:
-    su, sn = F.net_spec(Sol_NN), F.net_spec(PDE_NN)
-    tu, tn = F.net_tensors(Sol_NN), F.net_tensors(PDE_NN)
-    ss, flat, vu, vn, _ = F.collocation_loss_grad(su, tu, sn, tn, m, n, Collocation_Coords)
+def _loss_and_flat_grad(su, tu, sn, tn, m, n, Collocation_Coords, Data_Coords, Data_Values, private_ws=None):
+    """(loss, flat gradient, U views, N views) of Collocation_Loss + Data_Loss without an autograd graph."""
+    ws1 = private_ws[0] if private_ws is not None else None
+    ws2 = private_ws[1] if private_ws is not None else None
+    ss, flat, vu, vn, _ = F.collocation_loss_grad(su, tu, sn, tn, m, n, Collocation_Coords, private_ws=ws1)
     Coll = ss.reshape(()) / float(Collocation_Coords.shape[0])
     # data term: mean((U(x) - u)^2) (reference Loss_Functions.py:115-122; float64 targets promote the loss)
-    u = F.mlp_forward(su, tu, Data_Coords)
+    u = F.mlp_forward(su, tu, Data_Coords, private_ws=ws2)
     diff = u - Data_Values.reshape(-1)
     Data = (diff ** 2).mean()
-    F.mlp_backward_accumulate(su, tu, Data_Coords, (diff * (2.0 / diff.numel())).to(torch.float32), flat, 0)
+    F.mlp_backward_accumulate(su, tu, Data_Coords, (diff * (2.0 / diff.numel())).to(torch.float32), flat, 0,
+                              private_ws=ws2)
+    return (Coll.to(Data.dtype) + Data).detach(), flat, vu, vn
+
+
+def _fused_closure(Sol_NN, PDE_NN, m, n, Collocation_Coords, Data_Coords, Data_Values, Optimizer=None) -> torch.Tensor:
+    su, sn = F.net_spec(Sol_NN), F.net_spec(PDE_NN)
+    tu, tn = F.net_tensors(Sol_NN), F.net_tensors(PDE_NN)
+    Loss, flat, vu, vn = _loss_and_flat_grad(su, tu, sn, tn, m, n, Collocation_Coords, Data_Coords, Data_Values)
+    if Optimizer is not None and hasattr(Optimizer, "accept_flat_grad") and Optimizer.flat_layout_matches(tu + tn):
+        # multi-tensor optimiser (Optimizers.py): it reads the flat buffer directly, no per-tensor .grad traffic
+        Optimizer.accept_flat_grad(flat)
+        return Loss
     for p, g in zip(tu + tn, list(vu) + list(vn)):
         if p.grad is None:
             p.grad = g
         else:
             p.grad.add_(g)
-    return (Coll.to(Data.dtype) + Data).detach()
+    return Loss
+
+
+# ---- the whole epoch as one CUDA graph ---------------------------------------------------------------------------
+# At the reference's default sizes (5000 collocation + 4000 data points) an epoch is ~12 launches of 10-60 us of
+# work each: launch-bound.  With a multi-tensor optimiser (Optimizers.Fused_Adam / Fused_SGD) nothing in the epoch
+# needs the host -- the step count lives on the device -- so closure + optimiser step are captured once per
+# (networks, optimiser settings, point counts) and replayed: the epoch's points are copied into the graph's static
+# input buffers and one launch runs everything.  PDEREAD_TRAIN_GRAPH=0 switches the capture off.
+_TRAIN_GRAPH = os.environ.get("PDEREAD_TRAIN_GRAPH", "1") not in ("0", "", "off")
+_TRAIN_GRAPH_MAX_POINTS = int(os.environ.get("PDEREAD_TRAIN_GRAPH_MAX_POINTS", "65536"))
+_EPOCH_GRAPHS: dict = {}
+LAST_EPOCH_LOSS = None        # device scalar of the most recent graphed epoch (the closure's return value)
+
+
+def _graph_ok(Sol_NN, PDE_NN, Collocation_Coords, Optimizer) -> bool:
+    if not _TRAIN_GRAPH or not hasattr(Optimizer, "launch_step"):
+        return False
+    if Collocation_Coords.shape[0] > _TRAIN_GRAPH_MAX_POINTS:
+        return False
+    return Optimizer.flat_layout_matches(F.net_tensors(Sol_NN) + F.net_tensors(PDE_NN))
+
+
+def _graphed_epoch(Sol_NN, PDE_NN, m, n, Collocation_Coords, Data_Coords, Data_Values, Optimizer) -> torch.Tensor:
+    global LAST_EPOCH_LOSS
+    su, sn = F.net_spec(Sol_NN), F.net_spec(PDE_NN)
+    tu, tn = F.net_tensors(Sol_NN), F.net_tensors(PDE_NN)
+    dev = Collocation_Coords.device
+    g = Optimizer.param_groups[0]
+    hyper = tuple(sorted((k, str(v)) for k, v in g.items() if k != "params"))
+    key = (id(Optimizer), su, sn, m, n, Collocation_Coords.shape[0], Data_Coords.shape[0], Data_Values.dtype, dev.index,
+           hyper, tuple(t.data_ptr() for t in tu + tn))
+    ent = _EPOCH_GRAPHS.get(key)
+    if ent is None:
+        if len(_EPOCH_GRAPHS) >= 4:
+            _EPOCH_GRAPHS.pop(next(iter(_EPOCH_GRAPHS)))
+        s_coll, s_dc, s_dv = Collocation_Coords.clone(), Data_Coords.clone(), Data_Values.clone()
+        own_ws = [[], []]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):           # warm-up of the closure only (no optimiser step: parameters untouched)
+            for _ in range(2):
+                _loss_and_flat_grad(su, tu, sn, tn, m, n, s_coll, s_dc, s_dv, private_ws=own_ws)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            Loss, flat, vu, vn = _loss_and_flat_grad(su, tu, sn, tn, m, n, s_coll, s_dc, s_dv, private_ws=own_ws)
+            Optimizer.launch_step(flat)
+        for p, gv in zip(tu + tn, list(vu) + list(vn)):
+            p.grad = gv                          # .grad = views of the graph's static gradient buffer
+        ent = (graph, s_coll, s_dc, s_dv, Loss, flat, own_ws, [Data_Coords.data_ptr(), Data_Coords._version,
+                                                               Data_Values.data_ptr(), Data_Values._version])
+        _EPOCH_GRAPHS[key] = ent
+    graph, s_coll, s_dc, s_dv, Loss, flat, _ws, seen = ent
+    s_coll.copy_(Collocation_Coords)
+    now = [Data_Coords.data_ptr(), Data_Coords._version, Data_Values.data_ptr(), Data_Values._version]
+    if now != seen or s_dc.data_ptr() == 0:
+        s_dc.copy_(Data_Coords)
+        s_dv.copy_(Data_Values)
+        seen[:] = now
+    graph.replay()
+    LAST_EPOCH_LOSS = Loss
+    return Loss
+
+
+def release_epoch_graphs() -> None:
+    _EPOCH_GRAPHS.clear()
 
 
 def Discovery_Testing(

@@ -85,6 +85,17 @@ PROTOTYPES = {
     "pderead_rfe_workspace_bytes": (c_size_t, [c_int]),
     "pderead_rfe_gram": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_void_p]),
+    "pderead_input_moments": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "pderead_bn_fold": (c_int, [_NET, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pderead_bn_grad_sums": (c_int, [_NET, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pderead_bn_backward": (c_int, [_NET, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pderead_bn_input_grad": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "pderead_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                                  c_float, c_float, c_void_p, c_void_p]),
+    "pderead_sgd_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_int, c_float, c_float,
+                                 c_void_p, c_void_p]),
     "pderead_loss_tail_pack": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "pderead_loss_tail_unpack": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "pderead_generate_points": (c_int, [POINTER(c_double), c_int, c_int64, c_uint64, c_uint64, c_void_p, c_void_p]),

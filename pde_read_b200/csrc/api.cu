@@ -226,6 +226,249 @@ __global__ void loss_tail_unpack_kernel(const float* __restrict__ tail, double M
     }
 }
 
+// ---- input normalisation of the PDE network ("PDE Network - Normalize Inputs", reference Network.py:100-104,
+// 194-195: torch.nn.BatchNorm1d on the inputs of N) as a two-phase scheme --------------------------------------
+// phase 1: moments of the inputs over ALL points (per-CTA float64 partial sums; the host all-reduces the 1 + 2 din
+// numbers across ranks when the points are sharded); phase 2: the normalisation is an affine map of the inputs, so
+// it is folded into the first Linear layer (W0' = W0 diag(s), b0' = b0 + W0 (beta - s mu), s = gamma rstd) and the
+// unchanged MLP kernels run on the folded network.  The reverse pass maps the gradients of W0', b0' back to W0, b0,
+// gamma, beta and adds the batch-statistics terms to the input gradient: gin_pd += a_d + b_d x_pd.
+__global__ void __launch_bounds__(256) input_moments_kernel(const float* __restrict__ x, long long M, int din,
+                                                            double* __restrict__ mom) {
+    double s1[MAXD], s2[MAXD];
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) { s1[d] = 0.0; s2[d] = 0.0; }
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < M; p += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d)
+            if (d < din) {
+                const double v = (double)__ldg(x + p * din + d);
+                s1[d] += v;
+                s2[d] = fma(v, v, s2[d]);
+            }
+    }
+    __shared__ double red[2 * MAXD][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) {
+        if (d < din) {
+            double a = s1[d], b = s2[d];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (lane == 0) { red[d][warp] = a; red[MAXD + d][warp] = b; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * MAXD) {
+        const int d = threadIdx.x % MAXD, which = threadIdx.x / MAXD;
+        if (d < din) {
+            double a = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += red[which * MAXD + d][w];
+            atomicAdd(&mom[1 + which * din + d], a);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&mom[0], (double)M);
+}
+
+// stats = [mean (din) | rstd (din)]
+__global__ void __launch_bounds__(256) bn_fold_kernel(NetDev net, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const double* __restrict__ mom,
+                                                      int training, float momentum, float eps,
+                                                      float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                      long long* __restrict__ num_batches, float* __restrict__ w0f,
+                                                      float* __restrict__ b0f, float* __restrict__ stats) {
+    __shared__ float s_scale[MAXD], s_shift[MAXD];
+    const int din = net.din, W = net.W;
+    if (threadIdx.x < din) {
+        const int d = threadIdx.x;
+        float mean, var;
+        if (training) {
+            const double cnt = mom[0];
+            const double mu = mom[1 + d] / cnt;
+            double v = mom[1 + din + d] / cnt - mu * mu;        // biased variance normalises (torch BatchNorm1d)
+            if (v < 0.0) v = 0.0;
+            mean = (float)mu;
+            var = (float)v;
+            if (running_mean) running_mean[d] = (1.f - momentum) * running_mean[d] + momentum * mean;
+            if (running_var) {
+                const double unbiased = cnt > 1.0 ? v * cnt / (cnt - 1.0) : v;
+                running_var[d] = (1.f - momentum) * running_var[d] + momentum * (float)unbiased;
+            }
+        } else {
+            mean = running_mean[d];
+            var = running_var[d];
+        }
+        const float rstd = rsqrtf(var + eps);
+        stats[d] = mean;
+        stats[din + d] = rstd;
+        const float g = gamma ? gamma[d] : 1.f, b = beta ? beta[d] : 0.f;
+        s_scale[d] = g * rstd;
+        s_shift[d] = b - g * rstd * mean;
+    }
+    if (threadIdx.x == 0 && training && num_batches) num_batches[0] += 1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < W; i += blockDim.x) {
+        float acc = net.b[0][i];
+        for (int d = 0; d < din; ++d) {
+            const float w = net.w[0][(size_t)i * din + d];
+            w0f[(size_t)i * din + d] = w * s_scale[d];
+            acc = fmaf(w, s_shift[d], acc);
+        }
+        b0f[i] = acc;
+    }
+}
+
+// sums[d] = sum_i gW0'[i][d] W0[i][d],  sums[din + d] = sum_i gb0'[i] W0[i][d]   (float64; one block)
+__global__ void __launch_bounds__(256) bn_grad_sums_kernel(NetDev net, const float* __restrict__ gw0f,
+                                                           const float* __restrict__ gb0f, double* __restrict__ sums) {
+    const int din = net.din, W = net.W;
+    __shared__ double red[8];
+    for (int k = 0; k < 2 * din; ++k) {
+        const int d = k % din, which = k / din;
+        double a = 0.0;
+        for (int i = threadIdx.x; i < W; i += blockDim.x) {
+            const double w = (double)net.w[0][(size_t)i * din + d];
+            a += w * (which == 0 ? (double)gw0f[(size_t)i * din + d] : (double)gb0f[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+            sums[k] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// In place on the gradient slots of Layers.0.weight (gW0' -> gW0); gb0 = gb0' needs no work.  gamma / beta gradients
+// from the LOCAL sums (they are summed over ranks later with everything else); the input-gradient seeds a_d, b_d from
+// the GLOBAL sums and the global count.
+__global__ void __launch_bounds__(256) bn_backward_kernel(NetDev net, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ stats,
+                                                          const double* __restrict__ mom,
+                                                          const double* __restrict__ sums_local,
+                                                          const double* __restrict__ sums_global, int training,
+                                                          float* __restrict__ gw0, const float* __restrict__ gb0,
+                                                          float* __restrict__ ggamma, float* __restrict__ gbeta,
+                                                          float* __restrict__ seed_ab) {
+    __shared__ float s_scale[MAXD], s_shift[MAXD];
+    const int din = net.din, W = net.W;
+    if (threadIdx.x < din) {
+        const int d = threadIdx.x;
+        const float mean = stats[d], rstd = stats[din + d];
+        const float g = gamma ? gamma[d] : 1.f, b = beta ? beta[d] : 0.f;
+        s_scale[d] = g * rstd;
+        s_shift[d] = b - g * rstd * mean;
+        {   // parameters of the normalisation layer: local sums
+            const double S1 = sums_local[d], S2 = sums_local[din + d];
+            const double gs = S1 - (double)mean * S2;           // d loss / d s_d at fixed statistics
+            if (ggamma) ggamma[d] = (float)(gs * (double)rstd);
+            if (gbeta) gbeta[d] = (float)S2;
+        }
+        float a = 0.f, bq = 0.f;
+        if (training) {
+            const double S1 = sums_global[d], S2 = sums_global[din + d];
+            const double cnt = mom[0];
+            const double gs = S1 - (double)mean * S2;
+            const double gmu = -(double)(g * rstd) * S2;
+            const double gvar = gs * (double)g * (-0.5 * (double)rstd * (double)rstd * (double)rstd);
+            const double bd = 2.0 * gvar / cnt;
+            bq = (float)bd;
+            a = (float)(gmu / cnt - bd * (double)mean);
+        }
+        seed_ab[d] = a;
+        seed_ab[din + d] = bq;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < W * din; idx += blockDim.x) {
+        const int i = idx / din, d = idx - i * din;
+        gw0[idx] = fmaf(gw0[idx], s_scale[d], gb0[i] * s_shift[d]);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_input_grad_kernel(float* __restrict__ gin, const float* __restrict__ x,
+                                                            long long total, int din, const float* __restrict__ seed_ab) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(idx % din);
+        gin[idx] += fmaf(__ldg(seed_ab + din + d), __ldg(x + idx), __ldg(seed_ab + d));
+    }
+}
+
+// ---- multi-tensor optimiser steps on one flat buffer (reference main.py:63-71: torch.optim.Adam / SGD(momentum 0.9,
+// nesterov) over list(Sol_NN.parameters()) + list(PDE_NN.parameters()), stepped at Test_Train.py:105) -------------
+// state[0] = step count (float, like torch's state['step']), state[1] = blocks finished (ticket).  Every block reads
+// the old count, the last block to finish increments it: the kernel needs no host value that changes from step to
+// step, so it can be captured in a CUDA graph and replayed.
+// Same operation order as torch's single-tensor Adam: exp_avg.lerp_(g, 1-b1); exp_avg_sq.mul_(b2).addcmul_(g, g,
+// 1-b2); denom = sqrt(exp_avg_sq) / sqrt(1-b2^t) + eps; p.addcdiv_(exp_avg, denom, -lr/(1-b1^t)).
+__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, long long n,
+                                                        float lr, float b1, float b2, float eps, float wd,
+                                                        float grad_scale, float* __restrict__ state) {
+    const float t = state[0] + 1.f;
+    const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i] * grad_scale;
+        const float pi = p[i];
+        if (wd != 0.f) gi = fmaf(wd, pi, gi);
+        float mi = m[i], vi = v[i];
+        mi = fmaf(gi - mi, 1.f - b1, mi);
+        vi = fmaf(gi * gi, 1.f - b2, vi * b2);
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] = pi - step_size * (mi / denom);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(state + 1), 1u);
+        if (ticket == gridDim.x - 1) {
+            reinterpret_cast<unsigned int*>(state + 1)[0] = 0u;
+            state[0] = t;
+        }
+    }
+}
+
+// torch.optim.SGD with momentum, dampening 0: buf = g on the first step, else buf = mom*buf + g;
+// nesterov: d = g + mom*buf, else d = buf;  p -= lr*d.
+__global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ buf, long long n, float lr, float mom,
+                                                       int nesterov, float wd, float grad_scale,
+                                                       float* __restrict__ state) {
+    const bool first = (state[0] == 0.f);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i] * grad_scale;
+        const float pi = p[i];
+        if (wd != 0.f) gi = fmaf(wd, pi, gi);
+        float d = gi;
+        if (mom != 0.f) {
+            const float b = first ? gi : fmaf(mom, buf[i], gi);
+            buf[i] = b;
+            d = nesterov ? fmaf(mom, b, gi) : b;
+        }
+        p[i] = pi - lr * d;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(state + 1), 1u);
+        if (ticket == gridDim.x - 1) {
+            reinterpret_cast<unsigned int*>(state + 1)[0] = 0u;
+            state[0] = state[0] + 1.f;
+        }
+    }
+}
+
 __global__ void fma_probe_kernel(int variant, int iters, float* sink) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
     float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
@@ -1308,6 +1551,113 @@ int pderead_extraction_gram(const pderead_net* sol, const pderead_net* pde, int 
         if ((rc = plan_launch(pde->activation, 0, 0, plN, fn, s))) return rc;
         if ((rc = library_gram_launch(dxn, bb, mc, n, K, d_G, d_Atb, d_btb, s))) return rc;
     }
+    return PDEREAD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// input normalisation of the PDE network, two-phase (see the kernels above)
+// ------------------------------------------------------------------------------------------
+int pderead_input_moments(const float* d_x, int64_t M, int din, double* d_moments, void* stream) {
+    if (!d_moments || M < 0 || din < 1 || din > MAXD || (M > 0 && !d_x)) return PDEREAD_ERR_BAD_ARGUMENT;
+    if (M == 0) return PDEREAD_OK;
+    { const int rc_ = check_device(); if (rc_ != PDEREAD_OK) return rc_; }
+    const long long blocks = (M + 255) / 256;
+    input_moments_kernel<<<(int)(blocks < 592 ? blocks : 592), 256, 0, (cudaStream_t)stream>>>(d_x, (long long)M, din,
+                                                                                                d_moments);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark((cudaStream_t)stream, ST_BN);
+    return PDEREAD_OK;
+}
+
+int pderead_bn_fold(const pderead_net* net, const float* d_gamma, const float* d_beta, const double* d_moments,
+                    int training, float momentum, float eps, float* d_running_mean, float* d_running_var,
+                    int64_t* d_num_batches, float* d_w0_folded, float* d_b0_folded, float* d_stats, void* stream) {
+    NetDev N;
+    int rc = to_netdev(net, &N);
+    if (rc) return rc;
+    if (!d_w0_folded || !d_b0_folded || !d_stats) return PDEREAD_ERR_BAD_ARGUMENT;
+    if (training ? !d_moments : (!d_running_mean || !d_running_var)) return PDEREAD_ERR_BAD_ARGUMENT;
+    bn_fold_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(N, d_gamma, d_beta, d_moments, training, momentum, eps,
+                                                        d_running_mean, d_running_var, (long long*)d_num_batches,
+                                                        d_w0_folded, d_b0_folded, d_stats);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark((cudaStream_t)stream, ST_BN);
+    return PDEREAD_OK;
+}
+
+int pderead_bn_grad_sums(const pderead_net* net, const float* d_gw0_folded, const float* d_gb0_folded, double* d_sums,
+                         void* stream) {
+    NetDev N;
+    int rc = to_netdev(net, &N);
+    if (rc) return rc;
+    if (!d_gw0_folded || !d_gb0_folded || !d_sums) return PDEREAD_ERR_BAD_ARGUMENT;
+    bn_grad_sums_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(N, d_gw0_folded, d_gb0_folded, d_sums);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark((cudaStream_t)stream, ST_BN);
+    return PDEREAD_OK;
+}
+
+int pderead_bn_backward(const pderead_net* net, const float* d_gamma, const float* d_beta, const float* d_stats,
+                        const double* d_moments, const double* d_sums_local, const double* d_sums_global, int training,
+                        float* d_gw0, const float* d_gb0, float* d_ggamma, float* d_gbeta, float* d_seed_ab,
+                        void* stream) {
+    NetDev N;
+    int rc = to_netdev(net, &N);
+    if (rc) return rc;
+    if (!d_stats || !d_sums_local || !d_sums_global || !d_gw0 || !d_gb0 || !d_seed_ab || (training && !d_moments))
+        return PDEREAD_ERR_BAD_ARGUMENT;
+    bn_backward_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(N, d_gamma, d_beta, d_stats, d_moments, d_sums_local,
+                                                            d_sums_global, training, d_gw0, d_gb0, d_ggamma, d_gbeta,
+                                                            d_seed_ab);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark((cudaStream_t)stream, ST_BN);
+    return PDEREAD_OK;
+}
+
+int pderead_bn_input_grad(float* d_gin, const float* d_x, int64_t M, int din, const float* d_seed_ab, void* stream) {
+    if (M < 0 || din < 1 || din > MAXD || !d_seed_ab || (M > 0 && (!d_gin || !d_x))) return PDEREAD_ERR_BAD_ARGUMENT;
+    if (M == 0) return PDEREAD_OK;
+    { const int rc_ = check_device(); if (rc_ != PDEREAD_OK) return rc_; }
+    const long long total = (long long)M * din, blocks = (total + 255) / 256;
+    bn_input_grad_kernel<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, (cudaStream_t)stream>>>(d_gin, d_x, total, din,
+                                                                                                  d_seed_ab);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark((cudaStream_t)stream, ST_BN);
+    return PDEREAD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// optimiser step over all parameters of both networks in one launch
+// ------------------------------------------------------------------------------------------
+static int optim_blocks(int64_t n) {
+    const int64_t b = (n + 255) / 256;
+    return (int)(b < 1 ? 1 : (b > 592 ? 592 : b));
+}
+
+int pderead_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, float grad_scale, float* d_state2,
+                      void* stream) {
+    if (!d_params || !d_grads || !d_exp_avg || !d_exp_avg_sq || !d_state2 || n < 0) return PDEREAD_ERR_BAD_ARGUMENT;
+    if (n == 0) return PDEREAD_OK;
+    { const int rc_ = check_device(); if (rc_ != PDEREAD_OK) return rc_; }
+    adam_step_kernel<<<optim_blocks(n), 256, 0, (cudaStream_t)stream>>>(d_params, d_grads, d_exp_avg, d_exp_avg_sq,
+                                                                         (long long)n, lr, beta1, beta2, eps,
+                                                                         weight_decay, grad_scale, d_state2);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark((cudaStream_t)stream, ST_OPTIM);
+    return PDEREAD_OK;
+}
+
+int pderead_sgd_step(float* d_params, const float* d_grads, float* d_momentum_buf, int64_t n, float lr, float momentum,
+                     int nesterov, float weight_decay, float grad_scale, float* d_state2, void* stream) {
+    if (!d_params || !d_grads || !d_state2 || n < 0 || (momentum != 0.f && !d_momentum_buf)) return PDEREAD_ERR_BAD_ARGUMENT;
+    if (n == 0) return PDEREAD_OK;
+    { const int rc_ = check_device(); if (rc_ != PDEREAD_OK) return rc_; }
+    sgd_step_kernel<<<optim_blocks(n), 256, 0, (cudaStream_t)stream>>>(d_params, d_grads, d_momentum_buf, (long long)n,
+                                                                        lr, momentum, nesterov, weight_decay,
+                                                                        grad_scale, d_state2);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark((cudaStream_t)stream, ST_OPTIM);
     return PDEREAD_OK;
 }
 

@@ -69,15 +69,28 @@ static int build_table(int n, int K, LibTable* t, int32_t* indices /* [C][K] or 
     return PDEREAD_OK;
 }
 
-// LIB[c*GP + p] for one tile of GP points; D[(d)*GP + p] holds D_x^d U; valid[p] masks the tail.
-__device__ __forceinline__ void build_library_tile(const LibTable& t, const float* D, float* LIB, const float* mask) {
-    for (int idx = threadIdx.x; idx < GP; idx += blockDim.x) LIB[idx] = mask[idx];
+// LIB[c*TPN + p] for one tile of TPN points; D[(d)*TPN + p] holds D_x^d U; mask[p] masks the tail.
+// If AD != nullptr every column is also written widened to float64 into the Gram kernel's layout
+// AD[c / T][c % T][p] (group stride GST).
+template <int TPN, int T>
+__device__ __forceinline__ void build_library_tile(const LibTable& t, const float* D, float* LIB, const float* mask,
+                                                   double* AD, int GST) {
+    for (int idx = threadIdx.x; idx < TPN; idx += blockDim.x) {
+        const float v = mask[idx];
+        LIB[idx] = v;
+        if (AD) AD[idx] = (double)v;               // column 0 = group 0, row 0
+    }
     __syncthreads();
     for (int k = 1; k <= t.K; ++k) {
         const int lo = t.level_off[k], hi = t.level_off[k + 1];
-        for (int idx = threadIdx.x; idx < (hi - lo) * GP; idx += blockDim.x) {
-            const int c = lo + idx / GP, p = idx % GP;
-            LIB[c * GP + p] = LIB[t.parent[c] * GP + p] * D[t.last[c] * GP + p];
+        for (int idx = threadIdx.x; idx < (hi - lo) * TPN; idx += blockDim.x) {
+            const int c = lo + idx / TPN, p = idx % TPN;
+            const float v = LIB[t.parent[c] * TPN + p] * D[t.last[c] * TPN + p];
+            LIB[c * TPN + p] = v;
+            if (AD) {
+                const int g = c / T, r = c - g * T;
+                AD[(size_t)g * GST + r * TPN + p] = (double)v;
+            }
         }
         __syncthreads();
     }
@@ -99,7 +112,7 @@ __global__ void __launch_bounds__(256) library_dense_kernel(LibTable t, const fl
         }
         for (int idx = threadIdx.x; idx < GP; idx += blockDim.x) MASK[idx] = 1.f;
         __syncthreads();
-        build_library_tile(t, D, LIB, MASK);
+        build_library_tile<GP, 6>(t, D, LIB, MASK, nullptr, 0);
         for (int idx = threadIdx.x; idx < GP * t.C; idx += blockDim.x) {
             const int p = idx / t.C, c = idx - p * t.C;
             if (p0 + p < M) lib[(p0 + p) * t.C + c] = LIB[c * GP + p];
@@ -110,27 +123,34 @@ __global__ void __launch_bounds__(256) library_dense_kernel(LibTable t, const fl
 
 // Fused library + Gram of the augmented matrix [A | b] (CA = C + 1 columns), upper triangle only.
 //
-// The columns are cut into groups of T; a thread owns one T x T tile (gi <= gj) of [A|b]^T [A|b] in float64
+// The columns are cut into groups of T = 6; a thread owns one T x T tile (gi <= gj) of [A|b]^T [A|b] in float64
 // registers over all the point tiles of its CTA, so the symmetric half is never computed (C = 56: 1980 DFMA
 // per point instead of the 4096 of a full 64 x 64 block).  A CTA covers `ntile_cta` consecutive tiles of the
 // list (blockIdx.y selects the chunk; large libraries need several chunks for the register file) and SUB
 // sub-slices of the points of a tile (warp-uniform), and adds its result to the global system once at the end.
-// Shared layout of the widened tile: AD[group][row in group][point], strides (T*GP + 1, GP, 1) doubles: the odd
+// Point tiles are TPN = 128 points when the widened tile fits two CTAs per SM (the build / barrier phases between
+// two compute phases are latency-bound: ncu put `barrier` at 2.6 stalls per issue with 32-point tiles), else 32.
+// The derivatives of the NEXT tile are fetched into registers while the current one is being multiplied.
+// Shared layout of the widened tile: AD[group][row in group][point], strides (T*TPN + 1, TPN, 1) doubles: the odd
 // group stride spreads the groups a warp touches over the 16 8-byte banks.
-template <bool DENSE, int T>
-__global__ void __launch_bounds__(T == 8 ? 192 : 256, 2) gram_kernel(LibTable t, const float* __restrict__ src, const float* __restrict__ bvec,
-                                                   long long M, int ngroups, int ntile_total, int ntile_cta, int sub,
-                                                   double* __restrict__ G, double* __restrict__ Atb,
-                                                   double* __restrict__ btb) {
+constexpr int GT = 6;
+constexpr int GRAM_PRE = 6;      // prefetch registers per thread: (n + 2) * TPN / threads <= 6
+
+template <bool DENSE, int TPN>
+__global__ void __launch_bounds__(256, 2) gram_kernel(LibTable t, const float* __restrict__ src,
+                                                      const float* __restrict__ bvec, long long M, int ngroups,
+                                                      int ntile_total, int ntile_cta, int sub, double* __restrict__ G,
+                                                      double* __restrict__ Atb, double* __restrict__ btb) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    constexpr int GST = T * GP + 1;
+    constexpr int T = GT;
+    constexpr int GST = T * TPN + 1;
     const int C = t.C, CA = C + 1;
     const int nd = t.n + 1;
-    double* AD = reinterpret_cast<double*>(smraw);                    // [ngroups][T][GP] (+1 per group)
-    float* LIB = reinterpret_cast<float*>(AD + (size_t)ngroups * GST);   // [C][GP]
-    float* D = LIB + (size_t)C * GP;                                  // [(n+1)][GP]
-    float* MASK = D + nd * GP;                                        // [GP]
-    float* BV = MASK + GP;                                            // [GP]
+    double* AD = reinterpret_cast<double*>(smraw);                       // [ngroups][T][TPN] (+1 per group)
+    float* LIB = reinterpret_cast<float*>(AD + (size_t)ngroups * GST);   // [C][TPN]
+    float* D = LIB + (size_t)C * TPN;                                    // [(n+1)][TPN]
+    float* MASK = D + nd * TPN;                                          // [TPN]
+    float* BV = MASK + TPN;                                              // [TPN]
 
     // this thread's tile: index into the list of (gi <= gj) pairs, row-major over gi
     const int tiles_pad = (ntile_cta + 31) & ~31;
@@ -153,45 +173,78 @@ __global__ void __launch_bounds__(T == 8 ? 192 : 256, 2) gram_kernel(LibTable t,
 #pragma unroll
         for (int b = 0; b < T; ++b) acc[a][b] = 0.0;
 
-    const long long tiles = (M + GP - 1) / GP;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const long long p0 = tile * GP;
-        for (int idx = threadIdx.x; idx < GP; idx += blockDim.x) {
-            const bool ok = (p0 + idx < M);
-            MASK[idx] = ok ? 1.f : 0.f;
-            BV[idx] = ok ? bvec[p0 + idx] : 0.f;
+    // columns C+1 .. ngroups*T-1 of the last group are padding: zero once
+    for (int idx = threadIdx.x; idx < (ngroups * T - CA) * TPN; idx += blockDim.x) {
+        const int c = CA + idx / TPN, p = idx % TPN;
+        AD[(size_t)(c / T) * GST + (c % T) * TPN + p] = 0.0;
+    }
+
+    const long long tiles = (M + TPN - 1) / TPN;
+    const int nin = (nd + 1) * TPN;          // staged inputs of a tile: nd derivative rows + b
+    float pre[GRAM_PRE];
+    auto fetch = [&](long long tile) {
+        const long long p0 = tile * TPN;
+#pragma unroll
+        for (int u = 0; u < GRAM_PRE; ++u) {
+            const int idx = threadIdx.x + u * blockDim.x;
+            float v = 0.f;
+            if (idx < nin && tile < tiles) {
+                const int p = idx / (nd + 1), d = idx - p * (nd + 1);
+                if (p0 + p < M) v = (d < nd) ? __ldg(src + (p0 + p) * nd + d) : __ldg(bvec + p0 + p);
+            }
+            pre[u] = v;
         }
+    };
+    auto stage = [&](long long tile) {
+        const long long p0 = tile * TPN;
+#pragma unroll
+        for (int u = 0; u < GRAM_PRE; ++u) {
+            const int idx = threadIdx.x + u * blockDim.x;
+            if (idx < nin) {
+                const int p = idx / (nd + 1), d = idx - p * (nd + 1);
+                if (d < nd) D[d * TPN + p] = pre[u];
+                else BV[p] = pre[u];
+            }
+        }
+        for (int idx = threadIdx.x; idx < TPN; idx += blockDim.x) MASK[idx] = (p0 + idx < M) ? 1.f : 0.f;
+    };
+    if (!DENSE) {
+        fetch(blockIdx.x);
+        stage(blockIdx.x);
+    }
+    __syncthreads();
+
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long p0 = tile * TPN;
         if (DENSE) {
-            for (int idx = threadIdx.x; idx < GP * C; idx += blockDim.x) {
+            for (int idx = threadIdx.x; idx < TPN; idx += blockDim.x) {
+                const bool ok = (p0 + idx < M);
+                BV[idx] = ok ? bvec[p0 + idx] : 0.f;
+            }
+            for (int idx = threadIdx.x; idx < TPN * C; idx += blockDim.x) {
                 const int p = idx / C, c = idx - p * C;
-                LIB[c * GP + p] = (p0 + p < M) ? src[(p0 + p) * C + c] : 0.f;
+                const float v = (p0 + p < M) ? src[(p0 + p) * C + c] : 0.f;
+                const int g = c / T, r = c - g * T;
+                AD[(size_t)g * GST + r * TPN + p] = (double)v;
             }
             __syncthreads();
         } else {
-            for (int idx = threadIdx.x; idx < nd * GP; idx += blockDim.x) {
-                const int p = idx / nd, d = idx - p * nd;
-                D[d * GP + p] = (p0 + p < M) ? src[(p0 + p) * nd + d] : 0.f;
-            }
-            __syncthreads();
-            build_library_tile(t, D, LIB, MASK);
+            build_library_tile<TPN, T>(t, D, LIB, MASK, AD, GST);
         }
-        // widen to float64 (column C = b, columns beyond = 0)
-        for (int idx = threadIdx.x; idx < ngroups * T * GP; idx += blockDim.x) {
-            const int c = idx / GP, p = idx - c * GP;
-            const int g = c / T, r = c - g * T;
-            AD[(size_t)g * GST + r * GP + p] = (c < C) ? (double)LIB[c * GP + p] : (c == C ? (double)BV[p] : 0.0);
-        }
+        for (int idx = threadIdx.x; idx < TPN; idx += blockDim.x)
+            AD[(size_t)(C / T) * GST + (C % T) * TPN + idx] = (double)BV[idx];
         __syncthreads();
+        if (!DENSE) fetch(tile + gridDim.x);           // global loads in flight during the products
         if (has_tile) {
             const double* pa = AD + (size_t)gi * GST;
             const double* pb = AD + (size_t)gj * GST;
-#pragma unroll(T == 8 ? 1 : 2)
-            for (int p = my_sub; p < GP; p += sub) {
+#pragma unroll 2
+            for (int p = my_sub; p < TPN; p += sub) {
                 double av[T], bv[T];
 #pragma unroll
-                for (int a = 0; a < T; ++a) av[a] = pa[a * GP + p];
+                for (int a = 0; a < T; ++a) av[a] = pa[a * TPN + p];
 #pragma unroll
-                for (int b = 0; b < T; ++b) bv[b] = pb[b * GP + p];
+                for (int b = 0; b < T; ++b) bv[b] = pb[b * TPN + p];
 #pragma unroll
                 for (int a = 0; a < T; ++a)
 #pragma unroll
@@ -199,10 +252,14 @@ __global__ void __launch_bounds__(T == 8 ? 192 : 256, 2) gram_kernel(LibTable t,
             }
         }
         __syncthreads();
+        if (!DENSE) {
+            stage(tile + gridDim.x);
+            __syncthreads();
+        }
     }
 
     // combine the sub-slices in shared memory (reuses AD), then one float64 atomic per entry and CTA
-    double* RED = AD;      // [tiles_pad][T*T] (host sizes the buffer for it)
+    double* RED = AD;      // [T*T][tiles_pad] (host sizes the buffer for it)
     for (int s = 1; s < sub; ++s) {
         if (has_tile && my_sub == s) {
 #pragma unroll
@@ -240,65 +297,62 @@ __global__ void __launch_bounds__(T == 8 ? 192 : 256, 2) gram_kernel(LibTable t,
 }
 
 struct GramGeom {
-    int T, ngroups, ntile, nchunk, ntile_cta, sub, threads;
+    int tpn, ngroups, ntile, nchunk, ntile_cta, sub, threads;
     size_t smem;
 };
 
-static GramGeom gram_geometry(const LibTable& t) {
+static GramGeom gram_geometry(const LibTable& t, bool dense) {
     const int CA = t.C + 1;
-    GramGeom best;
-    memset(&best, 0, sizeof(best));
-    long best_work = -1;
-    const int Ts[2] = {8, 6};
+    GramGeom g;
+    memset(&g, 0, sizeof(g));
+    g.ngroups = (CA + GT - 1) / GT;
+    g.ntile = g.ngroups * (g.ngroups + 1) / 2;
+    const int cap = 256;                                       // tiles per CTA (128 registers per thread, 2 CTAs per SM)
+    g.nchunk = (g.ntile + cap - 1) / cap;
+    g.ntile_cta = (g.ntile + g.nchunk - 1) / g.nchunk;
+    const int pad = (g.ntile_cta + 31) & ~31;
+    g.sub = cap / pad;
+    if (g.sub < 1) g.sub = 1;
+    if (g.sub > 8) g.sub = 8;
+    g.threads = pad * g.sub;
+    const int tpns[2] = {128, 32};
     for (int k = 0; k < 2; ++k) {
-        GramGeom g;
-        g.T = Ts[k];
-        g.ngroups = (CA + g.T - 1) / g.T;
-        g.ntile = g.ngroups * (g.ngroups + 1) / 2;
-        const long work = (long)g.ntile * g.T * g.T;            // DFMA per point
-        const int cap = (g.T == 8) ? 192 : 256;                  // tiles per CTA (register file: 64 / 36 accumulators)
-        g.nchunk = (g.ntile + cap - 1) / cap;
-        g.ntile_cta = (g.ntile + g.nchunk - 1) / g.nchunk;
-        const int pad = (g.ntile_cta + 31) & ~31;
-        g.sub = cap / pad;
-        if (g.sub < 1) g.sub = 1;
-        if (g.sub > 8) g.sub = 8;
-        g.threads = pad * g.sub;
-        const size_t ad = sizeof(double) * (size_t)g.ngroups * (g.T * GP + 1);
-        const size_t red = g.sub > 1 ? sizeof(double) * (size_t)pad * g.T * g.T : 0;
-        g.smem = (ad > red ? ad : red) + sizeof(float) * ((size_t)t.C * GP + (t.n + 1) * GP + 2 * GP) + 16;
-        if (best_work < 0 || work < best_work) {
-            best_work = work;
-            best = g;
-        }
+        g.tpn = tpns[k];
+        const size_t ad = sizeof(double) * (size_t)g.ngroups * (GT * g.tpn + 1);
+        const size_t red = g.sub > 1 ? sizeof(double) * (size_t)pad * GT * GT : 0;
+        g.smem = (ad > red ? ad : red) + sizeof(float) * ((size_t)t.C * g.tpn + (t.n + 1) * g.tpn + 2 * g.tpn) + 16;
+        // the register prefetch must cover a tile's inputs
+        const bool pre_ok = dense || (size_t)(t.n + 2) * g.tpn <= (size_t)GRAM_PRE * g.threads;
+        if (g.smem <= 110 * 1024 && pre_ok) break;
     }
-    return best;
+    return g;
 }
 
 int gram_launch(const LibTable& t, bool dense, const float* src, const float* b, long long M, double* G, double* Atb,
                 double* btb, cudaStream_t s) {
     if (M <= 0) return PDEREAD_OK;
     { const int rc_ = check_device(); if (rc_ != PDEREAD_OK) return rc_; }
-    const GramGeom g = gram_geometry(t);
+    const GramGeom g = gram_geometry(t, dense);
+    if (!dense && (size_t)(t.n + 2) * g.tpn > (size_t)GRAM_PRE * g.threads) return PDEREAD_ERR_UNSUPPORTED_ORDER;
     int dev = 0, sms = 0;
     PDR_CUDA_CHECK(cudaGetDevice(&dev));
     PDR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const long long tiles = (M + GP - 1) / GP;
+    const long long tiles = (M + g.tpn - 1) / g.tpn;
     long long slices = ((long long)sms * 2 + g.nchunk - 1) / g.nchunk;
     if (slices > tiles) slices = tiles;
     if (slices < 1) slices = 1;
     dim3 grid((unsigned)slices, (unsigned)g.nchunk);
-#define PDR_GRAM_LAUNCH(DENSE_, T_)                                                                                   \
+#define PDR_GRAM_LAUNCH(DENSE_, TPN_)                                                                                 \
     do {                                                                                                              \
-        const int rc_ = ensure_dynamic_smem((const void*)gram_kernel<DENSE_, T_>, g.smem);                            \
+        const int rc_ = ensure_dynamic_smem((const void*)gram_kernel<DENSE_, TPN_>, g.smem);                          \
         if (rc_ != PDEREAD_OK) return rc_;                                                                            \
-        gram_kernel<DENSE_, T_><<<grid, g.threads, g.smem, s>>>(t, src, b, M, g.ngroups, g.ntile, g.ntile_cta, g.sub, \
-                                                                G, Atb, btb);                                         \
+        gram_kernel<DENSE_, TPN_><<<grid, g.threads, g.smem, s>>>(t, src, b, M, g.ngroups, g.ntile, g.ntile_cta,      \
+                                                                  g.sub, G, Atb, btb);                                \
     } while (0)
     if (dense) {
-        if (g.T == 8) PDR_GRAM_LAUNCH(true, 8); else PDR_GRAM_LAUNCH(true, 6);
+        if (g.tpn == 128) PDR_GRAM_LAUNCH(true, 128); else PDR_GRAM_LAUNCH(true, 32);
     } else {
-        if (g.T == 8) PDR_GRAM_LAUNCH(false, 8); else PDR_GRAM_LAUNCH(false, 6);
+        if (g.tpn == 128) PDR_GRAM_LAUNCH(false, 128); else PDR_GRAM_LAUNCH(false, 32);
     }
 #undef PDR_GRAM_LAUNCH
     PDR_CUDA_CHECK(cudaGetLastError());

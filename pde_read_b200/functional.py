@@ -267,7 +267,17 @@ def sol_derivatives_backward(spec: NetSpec, tensors, m: int, n: int, coords: tor
     return views
 
 
-def mlp_forward(spec: NetSpec, tensors, X: torch.Tensor) -> torch.Tensor:
+def _pick_ws(device, nb: int, private_ws: Optional[list]) -> torch.Tensor:
+    """The shared growable workspace, or (CUDA-graph capture: the graph keeps raw pointers) a buffer owned by the
+    caller's list that is never reallocated once the graph exists."""
+    if private_ws is None:
+        return workspace(device, nb)
+    if not private_ws or private_ws[0].numel() < nb:
+        private_ws[:] = [torch.empty(max(int(nb), 256), dtype=torch.uint8, device=device)]
+    return private_ws[0]
+
+
+def mlp_forward(spec: NetSpec, tensors, X: torch.Tensor, private_ws: Optional[list] = None) -> torch.Tensor:
     lib = _lib.load()
     X = _check_tensor(X.detach(), "network input")
     if X.dim() != 2 or X.shape[1] != spec.input_dim:
@@ -279,7 +289,7 @@ def mlp_forward(spec: NetSpec, tensors, X: torch.Tensor) -> torch.Tensor:
         if M == 0:
             return out
         nb = lib.pderead_mlp_workspace_bytes(ctypes.byref(s), M, 0)
-        ws = workspace(X.device, nb)
+        ws = _pick_ws(X.device, nb, private_ws)
         _lib.check(lib.pderead_mlp_forward(ctypes.byref(s), X.data_ptr(), M, out.data_ptr(), ws.data_ptr(), ws.numel(),
                                            _stream()), "pderead_mlp_forward")
     return out
@@ -306,7 +316,7 @@ def mlp_backward(spec: NetSpec, tensors, X: torch.Tensor, grad_out: torch.Tensor
 
 
 def mlp_backward_accumulate(spec: NetSpec, tensors, X: torch.Tensor, grad_out: torch.Tensor, flat: torch.Tensor,
-                            offset: int = 0) -> None:
+                            offset: int = 0, private_ws: Optional[list] = None) -> None:
     """Reverse pass of the plain MLP whose parameter gradients are ADDED (beta = 1) to the slots of this network
     inside an existing flat gradient buffer (layout of _grad_views at `offset`)."""
     lib = _lib.load()
@@ -319,7 +329,7 @@ def mlp_backward_accumulate(spec: NetSpec, tensors, X: torch.Tensor, grad_out: t
         g, _, _ = _grad_views(spec, tensors, flat, offset)
         go = _check_tensor(grad_out.reshape(-1), "grad of network output")
         nb = lib.pderead_mlp_workspace_bytes(ctypes.byref(s), _ws_points(M), 1)
-        ws = workspace(X.device, nb)
+        ws = _pick_ws(X.device, nb, private_ws)
         _lib.check(lib.pderead_mlp_backward(ctypes.byref(s), X.data_ptr(), M, go.data_ptr(), None, ctypes.byref(g),
                                             1.0, ws.data_ptr(), ws.numel(), _stream()), "pderead_mlp_backward")
 
@@ -372,13 +382,7 @@ def collocation_loss_grad(sol_spec, sol_tensors, pde_spec, pde_tensors, m: int, 
             return ss, flat, vu, vn, R
         gr = _check_tensor(grad_resid.reshape(-1), "grad of residual") if grad_resid is not None else None
         nb = lib.pderead_residual_workspace_bytes(ctypes.byref(su), ctypes.byref(sn), m, n, _ws_points(M), 1)
-        if private_ws is not None:
-            # (CUDA-graph capture: the graph keeps raw pointers, so it must not share the growable cached buffer)
-            if not private_ws or private_ws[0].numel() < nb:
-                private_ws[:] = [torch.empty(max(int(nb), 256), dtype=torch.uint8, device=coords.device)]
-            ws = private_ws[0]
-        else:
-            ws = workspace(coords.device, nb)
+        ws = _pick_ws(coords.device, nb, private_ws)
         _lib.check(lib.pderead_collocation_loss_grad(ctypes.byref(su), ctypes.byref(sn), m, n, coords.data_ptr(), M,
                                                      int(M_total), _ptr(gr), _ptr(R), ss.data_ptr(), ctypes.byref(gu),
                                                      ctypes.byref(gn), 0.0, ws.data_ptr(), ws.numel(), _stream()),
@@ -569,6 +573,134 @@ class CollocationLossFn(torch.autograd.Function):
             grads.append(scaled.as_strided(shape, _contig_strides(shape), off) if f else None)
             off += (numel + 3) // 4 * 4
         return (None, None, None, None, None, None, None, *grads)
+
+
+# ----------------------------------------------------------------------------------------------
+# input normalisation of the PDE network (Batch_Norm=True; reference Network.py:100-104,194-195), two-phase
+# ----------------------------------------------------------------------------------------------
+def input_moments(X: torch.Tensor, reducer=None) -> torch.Tensor:
+    """float64 [1 + 2 din]: point count, per-column sums and sums of squares of X, summed over the ranks when a
+    reducer (pde_read_b200.parallel.ShardReducer) is given."""
+    lib = _lib.load()
+    X = _check_tensor(X.detach(), "network input")
+    M, din = X.shape
+    with torch.cuda.device(X.device):
+        mom = torch.zeros(1 + 2 * din, dtype=torch.float64, device=X.device)
+        _lib.check(lib.pderead_input_moments(X.data_ptr(), M, din, mom.data_ptr(), _stream()), "pderead_input_moments")
+    if reducer is not None:
+        mom = reducer.reduce_moments(mom)
+    return mom
+
+
+class FoldedNet:
+    """A Batch_Norm=True network with its input normalisation folded into the first Linear layer for one call:
+    `tensors` is the parameter list the MLP kernels run on (folded copies in slots 0 and 1)."""
+
+    def __init__(self, net, moments: Optional[torch.Tensor], training: bool):
+        lib = _lib.load()
+        self.spec = net_spec(net, allow_input_norm=True)
+        self.orig = net_tensors(net)
+        bn = net.Norm_Layer
+        dev = self.orig[0].device
+        W, din = self.spec.width, self.spec.input_dim
+        self.training = bool(training)
+        self.moments = moments
+        self.gamma, self.beta = bn.weight, bn.bias
+        with torch.cuda.device(dev):
+            s, keep = _fill_net_uncached(self.spec, self.orig)
+            self.w0f = torch.empty((W, din), dtype=torch.float32, device=dev)
+            self.b0f = torch.empty((W,), dtype=torch.float32, device=dev)
+            self.stats = torch.empty((2 * din,), dtype=torch.float32, device=dev)
+            momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+            track = bn.track_running_stats and bn.running_mean is not None
+            if not self.training and not track:
+                raise PdereadError("eval-mode input normalisation needs running statistics")
+            _lib.check(lib.pderead_bn_fold(ctypes.byref(s), _ptr(self.gamma.detach() if self.gamma is not None else None),
+                                           _ptr(self.beta.detach() if self.beta is not None else None),
+                                           _ptr(moments), 1 if self.training else 0, momentum, float(bn.eps),
+                                           _ptr(bn.running_mean) if track else None,
+                                           _ptr(bn.running_var) if track else None,
+                                           _ptr(bn.num_batches_tracked) if (track and self.training) else None,
+                                           self.w0f.data_ptr(), self.b0f.data_ptr(), self.stats.data_ptr(), _stream()),
+                       "pderead_bn_fold")
+        self.tensors = [self.w0f, self.b0f] + list(self.orig[2:])
+
+    def backward_fixup(self, flat_views, X: torch.Tensor, gin: Optional[torch.Tensor], reducer=None):
+        """After the reverse pass of the folded network wrote its gradients into `flat_views` (slot 0 = gW0', slot 1 =
+        gb0'): rewrite slot 0 to gW0 in place, return (d gamma, d beta) and add the batch-statistics term to `gin`."""
+        lib = _lib.load()
+        dev = X.device
+        din = self.spec.input_dim
+        with torch.cuda.device(dev):
+            s, keep = _fill_net_uncached(self.spec, self.orig)
+            gw0, gb0 = flat_views[0], flat_views[1]
+            sums = torch.empty(2 * din, dtype=torch.float64, device=dev)
+            _lib.check(lib.pderead_bn_grad_sums(ctypes.byref(s), gw0.data_ptr(), gb0.data_ptr(), sums.data_ptr(), _stream()),
+                       "pderead_bn_grad_sums")
+            gsums = sums
+            if reducer is not None and self.training:
+                gsums = reducer.reduce_moments(sums.clone())
+            gg = torch.empty(din, dtype=torch.float32, device=dev)
+            gb = torch.empty(din, dtype=torch.float32, device=dev)
+            seed = torch.empty(2 * din, dtype=torch.float32, device=dev)
+            _lib.check(lib.pderead_bn_backward(ctypes.byref(s), _ptr(self.gamma.detach() if self.gamma is not None else None),
+                                               _ptr(self.beta.detach() if self.beta is not None else None),
+                                               self.stats.data_ptr(), _ptr(self.moments), sums.data_ptr(), gsums.data_ptr(),
+                                               1 if self.training else 0, gw0.data_ptr(), gb0.data_ptr(), gg.data_ptr(),
+                                               gb.data_ptr(), seed.data_ptr(), _stream()), "pderead_bn_backward")
+            if gin is not None and self.training:
+                Xc = _check_tensor(X.detach(), "network input")
+                _lib.check(lib.pderead_bn_input_grad(gin.data_ptr(), Xc.data_ptr(), Xc.shape[0], din, seed.data_ptr(),
+                                                     _stream()), "pderead_bn_input_grad")
+        return gg, gb
+
+
+class ShardedMeanSquareFn(torch.autograd.Function):
+    """mean(R^2) over the points of ALL ranks (R = this rank's residuals).  The value is all-reduced; the gradient
+    w.r.t. R is 2 R / M_total, so after backward() every rank holds its share of the parameter gradients and
+    ``parallel.all_reduce_grads`` sums them (the fused path without input normalisation does both in one packed
+    all-reduce; this one is the general-autograd path)."""
+
+    @staticmethod
+    def forward(ctx, R, reducer):
+        ss = (R.double() ** 2).sum().reshape(1)
+        red = reducer.reduce(None, ss, R.shape[0])
+        ctx.save_for_backward(R, red)
+        return (red[0] / red[1]).to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        R, red = ctx.saved_tensors
+        return (R * (2.0 * g * red[2].to(torch.float32))), None
+
+
+class BNInputMLPFn(torch.autograd.Function):
+    """out[M] = Neural_Network(X) for a Batch_Norm=True network (train or eval mode), differentiable in X, the
+    Linear / activation parameters and the normalisation layer's weight and bias."""
+
+    @staticmethod
+    def forward(ctx, X, net, reducer, gamma, beta, *tensors):
+        training = net.training
+        X = X.contiguous()
+        mom = input_moments(X, reducer) if training else None
+        if training and float(X.shape[0]) <= 1 and reducer is None:
+            raise ValueError("Expected more than 1 value per channel when training (input normalisation)")
+        fold = FoldedNet(net, mom, training)
+        out = mlp_forward(fold.spec, fold.tensors, X)
+        ctx.fold, ctx.reducer = fold, reducer
+        ctx.save_for_backward(X)
+        ctx.tensors = tensors
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (X,) = ctx.saved_tensors
+        fold = ctx.fold
+        gin, views = mlp_backward(fold.spec, fold.tensors, X, g_out, True)
+        gg, gb = fold.backward_fixup(views, X, gin, ctx.reducer)
+        grads = [v if t.requires_grad else None for v, t in zip(views, ctx.tensors)]
+        return (gin if ctx.needs_input_grad[0] else None, None, None,
+                gg if ctx.needs_input_grad[3] else None, gb if ctx.needs_input_grad[4] else None, *grads)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -19,6 +19,7 @@ import torch
 from .Data_Setup import Data_Loader
 from .Extraction import Extract_PDE, Print_Extracted_PDE
 from .Network import Neural_Network
+from .Optimizers import Fused_Adam, Fused_SGD
 from .Points import Generate_Points
 from .Settings_Reader import Settings_Reader
 from .Test_Train import Discovery_Testing, Discovery_Training
@@ -52,12 +53,14 @@ def main(root: str = "..", settings_path: str | None = None) -> None:
     Optimizer = None
     if Settings.Mode == "Discovery":
         Params = list(Sol_NN.parameters()) + list(PDE_NN.parameters())
+        # (reference main.py:63-71; Adam and SGD are the single-launch subclasses of the same torch classes, so the
+        #  Optimizer_State of a checkpoint keeps torch's layout)
         if Settings.Optimizer == "Adam":
-            Optimizer = torch.optim.Adam(Params, lr=Settings.Learning_Rate)
+            Optimizer = Fused_Adam(Params, lr=Settings.Learning_Rate)
         elif Settings.Optimizer == "LBFGS":
             Optimizer = torch.optim.LBFGS(Params, lr=Settings.Learning_Rate)
         elif Settings.Optimizer == "SGD":
-            Optimizer = torch.optim.SGD(Params, lr=Settings.Learning_Rate, momentum=0.9, nesterov=True)
+            Optimizer = Fused_SGD(Params, lr=Settings.Learning_Rate, momentum=0.9, nesterov=True)
         else:
             print("Optimizer is %s when it should be \"Adam\", \"LBFGS\", or \"SGD\"" % Settings.Optimizer)
             print("Aborting.")

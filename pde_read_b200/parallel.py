@@ -116,6 +116,21 @@ class ShardReducer:
         return moments
 
 
+def all_reduce_grads(params, reducer: "ShardReducer") -> None:
+    """Sum the .grad of `params` over the ranks in one all-reduce (general autograd path, e.g. a Batch_Norm=True PDE
+    network; the fused collocation path reduces its flat buffer itself)."""
+    ps = [p for p in params if p.grad is not None]
+    if not ps:
+        return
+    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=reducer.group)
+    off = 0
+    for p in ps:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+
+
 def sharded_loss_and_grads(local_fn: Callable[[torch.Tensor, int], Tuple[torch.Tensor, torch.Tensor]],
                            coords: torch.Tensor, reducer: ShardReducer) -> Tuple[float, torch.Tensor]:
     """Reference semantics of a sharded collocation step, independent of where the arithmetic runs.

@@ -231,9 +231,75 @@ def golden_extract_k5():
     print("margins", np.round(margin, 4))
 
 
+def golden_batchnorm():
+    """PDE network with "Normalize Inputs" (Network.py:100-104,194-195: BatchNorm1d on the inputs of N) through the
+    unmodified reference: train-mode collocation loss + every gradient (incl. Norm_Layer.weight / .bias) + the running
+    statistics after the call, then the eval-mode loss."""
+    torch.manual_seed(321)
+    m, n, M = 1, 2, 80
+    U = Network.Neural_Network(3, 20, 2, 1, Activation_Function="Tanh")
+    N = Network.Neural_Network(2, 16, n + 1, 1, Activation_Function="Rational", Batch_Norm=True)
+    with torch.no_grad():
+        for net in (U, N):
+            for k, p in net.named_parameters():
+                if k.endswith(".bias") and not k.startswith("Norm_Layer"):
+                    p.uniform_(-0.3, 0.3)
+        N.Norm_Layer.weight.copy_(torch.tensor([1.3, 0.7, 1.1]))
+        N.Norm_Layer.bias.copy_(torch.tensor([0.1, -0.2, 0.05]))
+    P = torch.rand((M, 2)) * torch.tensor([2.0, 3.0]) + torch.tensor([0.0, -1.5])
+    out = dict(coords=P.numpy())
+    out.update(state_np("sol.", U))
+    out.update(state_np("pde.", N))          # includes Norm_Layer.* and the initial running statistics
+    U.train(); N.train()
+    loss = Loss_Functions.Collocation_Loss(U, N, m, n, P.clone())
+    loss.backward()
+    out["loss_train"] = np.float64(loss.item())
+    out.update(grads_np("gsol.", U))
+    out.update(grads_np("gpde.", N))
+    out["running_mean_after"] = N.Norm_Layer.running_mean.numpy().copy()
+    out["running_var_after"] = N.Norm_Layer.running_var.numpy().copy()
+    out["num_batches_after"] = np.int64(N.Norm_Layer.num_batches_tracked.item())
+    U.eval(); N.eval()
+    out["loss_eval"] = np.float64(Loss_Functions.Collocation_Loss(U, N, m, n, P.clone()).item())
+    np.savez_compressed(os.path.join(HERE, "batchnorm_rat_m1n2.npz"), **out)
+    print("batchnorm: train loss", out["loss_train"], "eval loss", out["loss_eval"], "running mean", out["running_mean_after"])
+
+
+def golden_stock_artifacts():
+    """The reference's own artifacts for the end-to-end drop-in test, as DATA: the text of its stock
+    Settings.txt with only the four lines a user must touch to extract from the shipped checkpoint on a GPU changed
+    (load both networks, Extraction mode, GPU), the Adam state of the shipped checkpoint for two parameter tensors
+    (layout check), and a slice of the shipped data set (the driver needs Input_Bounds and the four arrays)."""
+    with open(os.path.join(REF, "Settings.txt")) as fh:
+        text = fh.read()
+    edits = (("Load Sol Network State [bool] :                  False", "Load Sol Network State [bool] :                  True"),
+             ("Load PDE Network State [bool] :                  False", "Load PDE Network State [bool] :                  True"),
+             ("Discovery, or Extraction mode [str] :            Discovery", "Discovery, or Extraction mode [str] :            Extraction"),
+             ("Train on CPU or GPU [GPU, CPU] :                 CPU", "Train on CPU or GPU [GPU, CPU] :                 GPU"))
+    for a, b in edits:
+        assert text.count(a) == 1, a
+        text = text.replace(a, b)
+    d = np.load(os.path.join(REF, "Data", "DataSets", "Burgers_Sine_N50_P5000.npz"))
+    saved = torch.load(os.path.join(REF, "Saves", "Burgers_Sine_N50_P5000_Rat_Adam"), map_location="cpu")
+    opt = saved["Optimizer_State"]
+    np.savez_compressed(os.path.join(HERE, "stock_artifacts.npz"),
+                        settings_text=np.frombuffer(text.encode(), dtype=np.uint8),
+                        Train_Inputs=d["Train_Inputs"][:512], Train_Targets=d["Train_Targets"][:512],
+                        Test_Inputs=d["Test_Inputs"][:128], Test_Targets=d["Test_Targets"][:128],
+                        Input_Bounds=d["Input_Bounds"],
+                        opt_step=np.float64(float(opt["state"][0]["step"])),
+                        opt_exp_avg_0=opt["state"][0]["exp_avg"].numpy(), opt_exp_avg_sq_0=opt["state"][0]["exp_avg_sq"].numpy(),
+                        opt_num_params=np.int64(len(opt["param_groups"][0]["params"])),
+                        opt_lr=np.float64(opt["param_groups"][0]["lr"]))
+    print("stock artifacts: settings %d bytes, optimizer step %s, %d params" % (len(text), opt["state"][0]["step"],
+                                                                                 len(opt["param_groups"][0]["params"])))
+
+
 if __name__ == "__main__":
     golden_checkpoint()
     golden_random()
     golden_library_small()
     golden_extract_k5()
+    golden_batchnorm()
+    golden_stock_artifacts()
     print("done")

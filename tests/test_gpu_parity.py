@@ -510,3 +510,118 @@ def test_gradients_over_odd_shapes(act, LU, WU, LN, WN, m, n):
     for pref, net, g32, g64 in (("u.", U, gs32, gs64), ("n.", N, gp32, gp64)):
         for k, g in grads_of(net).items():
             assert_close_to_reference(g, g32[k].numpy(), g64[k].numpy(), TOL_GRAD, pref + k)
+
+
+def _bn_nets_from_golden(z):
+    from pde_read_b200.Network import Neural_Network
+    su, sn = split_state(z, "sol."), split_state(z, "pde.")
+    U = make_net(su, "Tanh", 2)
+    N = Neural_Network(2, 16, 3, 1, Device=DEV, Activation_Function="Rational", Batch_Norm=True)
+    N.load_state_dict({k: v.to(DEV) for k, v in sn.items()})
+    return U, N, su, sn
+
+
+def test_pde_network_input_batch_norm_golden():
+    """Same feature against the UNMODIFIED reference (tests/golden/batchnorm_rat_m1n2.npz, make_golden.golden_batchnorm):
+    train-mode loss, every gradient incl. Norm_Layer.weight / .bias, running statistics after the call, eval-mode loss.
+    No torch BatchNorm1d runs on this path: the layer only holds parameters and buffers."""
+    from pde_read_b200.Loss_Functions import Collocation_Loss
+    z = load_golden("batchnorm_rat_m1n2.npz")
+    U, N, su, sn = _bn_nets_from_golden(z)
+    P = torch.from_numpy(z["coords"]).to(DEV)
+    called = {"n": 0}
+    orig = torch.nn.BatchNorm1d.forward
+
+    def spy(self, x):
+        called["n"] += 1
+        return orig(self, x)
+
+    torch.nn.BatchNorm1d.forward = spy
+    try:
+        U.train(); N.train()
+        loss = Collocation_Loss(U, N, 1, 2, P, torch.float32, DEV)
+        loss.backward()
+    finally:
+        torch.nn.BatchNorm1d.forward = orig
+    assert called["n"] == 0
+    assert abs(loss.item() - float(z["loss_train"])) <= 2e-5 * float(z["loss_train"])
+    scale = max(float(np.abs(z[k]).max()) for k in z.files if k.startswith("gsol.") or k.startswith("gpde."))
+    for prefix, net in (("gsol.", U), ("gpde.", N)):
+        for k, g in grads_of(net).items():
+            ref = z[prefix + k]
+            if np.abs(ref).max() < 1e-5 * scale:
+                assert np.abs(g).max() < 3e-5 * scale, k
+            else:
+                assert rel_err(g, ref) < 3e-4, (k, rel_err(g, ref))
+    assert rel_err(N.Norm_Layer.running_mean.cpu().numpy(), z["running_mean_after"]) < 1e-5
+    assert rel_err(N.Norm_Layer.running_var.cpu().numpy(), z["running_var_after"]) < 1e-5
+    assert int(N.Norm_Layer.num_batches_tracked.item()) == int(z["num_batches_after"])
+    U.eval(); N.eval()
+    with torch.no_grad():
+        l_eval = Collocation_Loss(U, N, 1, 2, P, torch.float32, DEV).item()
+    assert abs(l_eval - float(z["loss_eval"])) <= 2e-5 * float(z["loss_eval"])
+
+
+class _ScriptedReducer:
+    """Stands in for ShardReducer on ONE GPU: collective number k of a shard's step returns the recorded sum over
+    the shards once it is known (replay), and records this shard's contribution otherwise."""
+    TAIL = 4
+
+    def __init__(self, script):
+        self.script, self.i, self.log = script, 0, []
+
+    def _next(self, local):
+        k = self.i
+        self.i += 1
+        self.log.append(local.clone())
+        return self.script[k].clone() if k < len(self.script) else local
+
+    def reduce_moments(self, t):
+        return self._next(t)
+
+    def reduce(self, flat, ss, M):
+        assert flat is None
+        both = self._next(torch.cat([ss.double().reshape(1), torch.tensor([float(M)], dtype=torch.float64, device=ss.device)]))
+        return torch.cat([both, 1.0 / both[1:2]])
+
+
+def test_input_batch_norm_sharded_matches_single_process():
+    """Points split over two 'ranks' (run one after the other on this GPU with scripted collectives: moments of the
+    inputs, loss, backward sums): summed gradients and loss equal the single-process result."""
+    from pde_read_b200 import Loss_Functions
+    from pde_read_b200.Loss_Functions import Collocation_Loss
+    z = load_golden("batchnorm_rat_m1n2.npz")
+    P = torch.from_numpy(z["coords"]).to(DEV)
+    shards = [P[:47].contiguous(), P[47:].contiguous()]
+    U, N, su, sn = _bn_nets_from_golden(z)
+    U.train(); N.train()
+    Collocation_Loss(U, N, 1, 2, P, torch.float32, DEV).backward()
+    want = {**{"U." + k: g for k, g in grads_of(U).items()}, **{"N." + k: g for k, g in grads_of(N).items()}}
+    want_rm = N.Norm_Layer.running_mean.clone()
+
+    script = []
+    try:
+        for stage in range(4):          # collectives of a step: [moments, loss, backward sums]
+            logs, outs = [], []
+            for sh in shards:
+                U, N, _, _ = _bn_nets_from_golden(z)
+                U.train(); N.train()
+                red = _ScriptedReducer(script)
+                Loss_Functions.set_reducer(red)
+                loss = Collocation_Loss(U, N, 1, 2, sh, torch.float32, DEV)
+                loss.backward()
+                logs.append(red.log)
+                outs.append((loss.item(), {**{"U." + k: g for k, g in grads_of(U).items()},
+                                           **{"N." + k: g for k, g in grads_of(N).items()}},
+                             N.Norm_Layer.running_mean.clone()))
+            if stage < 3:
+                script = script + [logs[0][stage] + logs[1][stage]]
+    finally:
+        Loss_Functions.set_reducer(None)
+    assert len(logs[0]) == 3
+    assert abs(outs[0][0] - float(z["loss_train"])) <= 2e-5 * float(z["loss_train"]) and outs[0][0] == outs[1][0]
+    scale = max(float(np.abs(v).max()) for v in want.values())
+    for k, ref in want.items():
+        got = outs[0][1][k] + outs[1][1][k]
+        assert np.abs(got - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-3 * scale), k
+    assert torch.allclose(outs[0][2], want_rm, rtol=1e-5, atol=1e-7) and torch.allclose(outs[1][2], want_rm, rtol=1e-5, atol=1e-7)
