@@ -1,5 +1,5 @@
 """Dev tool (GPU): wall time of one Discovery_Training epoch (Adam) at the reference's default sizes, with the
-graph-free closure and with the autograd closure."""
+autograd closure, the graph-free closure, the single-launch Fused_Adam, and the whole epoch replayed from one CUDA graph."""
 import sys
 import time
 
@@ -9,6 +9,7 @@ sys.path.insert(0, ".")
 from oracle import pde_read_oracle as orc          # noqa: E402  (weights init only)
 from pde_read_b200 import Test_Train                # noqa: E402
 from pde_read_b200.Network import Neural_Network    # noqa: E402
+from pde_read_b200.Optimizers import Fused_Adam     # noqa: E402
 
 dev = torch.device("cuda:0")
 
@@ -40,3 +41,24 @@ for M, Md in ((5000, 4000), (50000, 20000)):
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / K
             print("M=%d Md=%d fast_closure=%s adam_fused=%s: %.1f us/epoch" % (M, Md, fast, fused, dt * 1e6), flush=True)
+
+    Test_Train._FAST_CLOSURE = True
+    for graph in (False, True):
+        Test_Train._TRAIN_GRAPH = graph
+        Test_Train.release_epoch_graphs()
+        U = mk(orc.init_network(5, 50, 2, "Rational", seed=1), "Rational", 2)
+        N = mk(orc.init_network(2, 100, 3, "Rational", seed=2), "Rational", 3)
+        opt = Fused_Adam(list(U.parameters()) + list(N.parameters()), lr=1e-3)
+        Xd = torch.rand(Md, 2, device=dev)
+        yd = torch.rand(Md, device=dev, dtype=torch.float64)
+        Ps = [torch.rand(M, 2, device=dev) for _ in range(8)]      # new collocation points every epoch, as main.py does
+        for i in range(30):
+            Test_Train.Discovery_Training(U, N, 1, 2, Ps[i % 8], Xd, yd, opt, torch.float32, dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        K = 300
+        for i in range(K):
+            Test_Train.Discovery_Training(U, N, 1, 2, Ps[i % 8], Xd, yd, opt, torch.float32, dev)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / K
+        print("M=%d Md=%d Fused_Adam whole-epoch graph=%s: %.1f us/epoch" % (M, Md, graph, dt * 1e6), flush=True)

@@ -30,7 +30,8 @@ torch.set_num_threads(8)
 
 
 def state_np(prefix, net):
-    return {prefix + k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
+    # (copies: BatchNorm buffers are updated in place by a later forward pass)
+    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in net.state_dict().items()}
 
 
 def grads_np(prefix, net):
