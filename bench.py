@@ -586,7 +586,12 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
+    real_stdout = None
     if world > 1:
+        # NCCL may print its version banner on stdout: keep stdout clean for the ONE JSON line (fd 1 -> stderr until then)
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # the exchange is one 84..330 KB all-reduce per step: latency-bound, and NCCL's default choice for it on
         # 8 NVSwitch GPUs (ring, LL) is slower than the tree (measured: C2 step 1.71 -> 1.68 ms, e2e +6 %)
@@ -628,6 +633,9 @@ def main():
         if world == 1 and not args.no_cpu_baseline and not args.config:
             _, _, sd_u, sd_n = build_nets(c, torch.device("cpu"))
             line["reference_on_b200"] = time_reference_on_gpu(c, sd_u, sd_n, dev, 20000)
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
