@@ -152,7 +152,9 @@ __global__ void __launch_bounds__(256, 2) gram_kernel(LibTable t, const float* _
     float* MASK = D + nd * TPN;                                          // [TPN]
     float* BV = MASK + TPN;                                              // [TPN]
 
-    // this thread's tile: index into the list of (gi <= gj) pairs, row-major over gi
+    // this thread's tile: index into the list of (gi <= gj) pairs, row-major over gi; the tile count is padded to a
+    // warp so that a warp works on ONE sub-slice (measured: packing (sub-slice, tile) densely -- 220 of 224 lanes busy
+    // at C = 56 instead of 220 of 256 -- is 3 % slower: lanes of different sub-slices read different points)
     const int tiles_pad = (ntile_cta + 31) & ~31;
     const int my_sub = threadIdx.x / tiles_pad;
     const int tl = threadIdx.x - my_sub * tiles_pad;
@@ -314,7 +316,8 @@ static GramGeom gram_geometry(const LibTable& t, bool dense) {
     g.sub = cap / pad;
     if (g.sub < 1) g.sub = 1;
     if (g.sub > 8) g.sub = 8;
-    g.threads = pad * g.sub;
+    g.threads = (pad * g.sub + 31) & ~31;
+    if (g.threads < 64) g.threads = 64;                       // (the register prefetch needs (n + 2) * 32 / 6 threads)
     const int tpns[2] = {128, 32};
     for (int k = 0; k < 2; ++k) {
         g.tpn = tpns[k];
@@ -390,6 +393,8 @@ int library_gram_launch(const float* dxn, const float* b, long long M, int n, in
 // of the library without it.  A zero column gets coefficient 0 (the reference divides by its zero norm -> NaN).
 // ---------------------------------------------------------------------------------------------
 constexpr double RFE_PIV_TOL = 1e-13;
+// RFE_MLP (template): independent matrix loads in flight per thread in the rank-1 updates: 1 when the matrix is in shared
+// memory, 4 when it lives in global memory (C = 252: 8.7 -> 5.4 ms)
 
 struct ArgBest {
     float v;
@@ -414,6 +419,7 @@ __device__ __forceinline__ ArgBest block_argmin_from_partials(const float* pv, c
     return warp_argmin(b);
 }
 
+template <int RFE_MLP>
 __global__ void __launch_bounds__(1024) rfe_kernel(const double* __restrict__ G, const double* __restrict__ Atb,
                                                    const double* __restrict__ btb, int C, float* __restrict__ X,
                                                    float* __restrict__ residual, int* __restrict__ order,
@@ -485,13 +491,27 @@ __global__ void __launch_bounds__(1024) rfe_kernel(const double* __restrict__ G,
         for (int j = tid; j < LD; j += nt) hv[j] = Tm[(size_t)k * LD + j];
         __syncthreads();
         const double inv_d = 1.0 / d;
-        for (int idx = tid; idx < LD * LD; idx += nt) {
-            const int i = (int)(((float)idx + 0.5f) * inv_ld), j = idx - i * LD;
-            double v;
-            if (i == k) v = (j == k) ? -inv_d : hv[j] * inv_d;
-            else if (j == k) v = hv[i] * inv_d;
-            else v = fma(-hv[i] * inv_d, hv[j], Tm[idx]);
-            Tm[idx] = v;
+        // (batches of RFE_MLP independent loads, then the stores: when the matrix lives in global memory -- C > ~160 --
+        //  a step is bound by the L2 round trip, and the compiler cannot hoist loads over stores to the same array)
+        for (int base = tid; base < LD * LD; base += RFE_MLP * nt) {
+            double cur[RFE_MLP];
+#pragma unroll
+            for (int u = 0; u < RFE_MLP; ++u) {
+                const int idx = base + u * nt;
+                cur[u] = idx < LD * LD ? Tm[idx] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < RFE_MLP; ++u) {
+                const int idx = base + u * nt;
+                if (idx < LD * LD) {
+                    const int i = (int)(((float)idx + 0.5f) * inv_ld), j = idx - i * LD;
+                    double v;
+                    if (i == k) v = (j == k) ? -inv_d : hv[j] * inv_d;
+                    else if (j == k) v = hv[i] * inv_d;
+                    else v = fma(-hv[i] * inv_d, hv[j], cur[u]);
+                    Tm[idx] = v;
+                }
+            }
         }
         ArgBest b;
         b.v = INFINITY; b.i = 0x7fffffff;
@@ -569,10 +589,23 @@ __global__ void __launch_bounds__(1024) rfe_kernel(const double* __restrict__ G,
         __syncthreads();
         const double inv_d = 1.0 / d;
         const float inv_m = 1.0f / (float)m;
-        for (int idx = tid; idx < m * m; idx += nt) {
-            const int a = (int)(((float)idx + 0.5f) * inv_m), b2 = idx - a * m;
-            double* e = Tm + (size_t)act[a] * LD + act[b2];
-            *e = fma(-hv[a] * inv_d, hv[b2], *e);
+        for (int base = tid; base < m * m; base += RFE_MLP * nt) {
+            double cur[RFE_MLP];
+            double* e[RFE_MLP];
+            int ia[RFE_MLP], ib[RFE_MLP];
+#pragma unroll
+            for (int u = 0; u < RFE_MLP; ++u) {
+                const int idx = base + u * nt;
+                const bool ok = idx < m * m;
+                const int a = ok ? (int)(((float)idx + 0.5f) * inv_m) : 0;
+                ia[u] = a;
+                ib[u] = ok ? idx - a * m : 0;
+                e[u] = Tm + (size_t)act[ia[u]] * LD + act[ib[u]];
+                cur[u] = ok ? *e[u] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < RFE_MLP; ++u)
+                if (base + u * nt < m * m) *e[u] = fma(-hv[ia[u]] * inv_d, hv[ib[u]], cur[u]);
         }
         ArgBest b;
         b.v = INFINITY; b.i = 0x7fffffff;
@@ -695,12 +728,17 @@ int pderead_rfe_gram(const double* d_G, const double* d_Atb, const double* d_btb
     const int use_smem = (small + mat + 1024 <= (size_t)maxsm) ? 1 : 0;
     if (!use_smem && (!ws || ws_bytes < mat)) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
     const size_t smem = use_smem ? small + mat : small;
-    { const int rc_ = ensure_dynamic_smem((const void*)rfe_kernel, smem); if (rc_ != PDEREAD_OK) return rc_; }
+    const void* kern = use_smem ? (const void*)rfe_kernel<1> : (const void*)rfe_kernel<4>;
+    { const int rc_ = ensure_dynamic_smem(kern, smem); if (rc_ != PDEREAD_OK) return rc_; }
     int threads = (((C + 1) * (C + 1) / 8) + 31) & ~31;     // ~8 matrix entries per thread and step
     if (threads < 128) threads = 128;
     if (threads > 1024) threads = 1024;
-    rfe_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(d_G, d_Atb, d_btb, C, d_X, d_residual, d_order, d_rank, d_change,
-                                                        (double*)ws, use_smem);
+    if (use_smem)
+        rfe_kernel<1><<<1, threads, smem, (cudaStream_t)stream>>>(d_G, d_Atb, d_btb, C, d_X, d_residual, d_order, d_rank,
+                                                                   d_change, (double*)ws, 1);
+    else
+        rfe_kernel<4><<<1, threads, smem, (cudaStream_t)stream>>>(d_G, d_Atb, d_btb, C, d_X, d_residual, d_order, d_rank,
+                                                                   d_change, (double*)ws, 0);
     PDR_CUDA_CHECK(cudaGetLastError());
     stage_mark((cudaStream_t)stream, ST_RFE);
     return PDEREAD_OK;
