@@ -243,6 +243,10 @@ int pderead_debug_stage_events_recorded(void);
  * 4 plain-MLP reverse, 5 jet reverse, 6 partial-gradient reduction, 7 library + Gram, 8 RFE + ranking,
  * 9 optimiser step, 10 input-normalisation helpers.  Fills h_tags[0..return value). */
 int pderead_debug_stage_tags(int32_t* h_tags, int capacity);
+/* Plain-MLP forward launches (jet length 1: the PDE network, Data_Loss) use the register-tiled kernel with the
+ * layer's weights staged in shared memory (on, default) or the lane = point kernel (off; also PDEREAD_PLAIN_MLP=0).
+ * A measurement switch; both produce the same numbers up to summation order.  Returns the previous setting. */
+int pderead_debug_set_plain_mlp(int on);
 /* Tensor-core policy for the hidden-layer products (tcgen05, 3xTF32; widths 8..128, depth >= 2):
  *   0 off   - CUDA-core kernels everywhere;
  *   1 auto  - default: forward-only calls of networks wider than 64 (>= 3 hidden layers) use the tensor cores, the gradient

@@ -104,6 +104,7 @@ PROTOTYPES = {
     "pderead_debug_stage_events_recorded": (c_int, []),
     "pderead_debug_stage_tags": (c_int, [POINTER(c_int32), c_int]),
     "pderead_debug_set_tensor_cores": (c_int, [c_int]),
+    "pderead_debug_set_plain_mlp": (c_int, [c_int]),
 }
 
 _lib = None

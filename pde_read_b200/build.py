@@ -31,7 +31,7 @@ CFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-I", 
 # plain MLP (0,0) and every combination with a time series (Evaluate_Derivatives always has m >= 1).
 FWD_COMBOS = [(0, 0), (1, 0), (2, 0), (3, 0), (4, 0), (1, 1), (2, 1), (3, 1), (4, 1), (1, 2), (2, 2), (3, 2), (4, 2)]
 BWD_COMBOS = {(0, 0), (1, 1), (2, 1), (3, 1), (4, 1), (1, 2), (2, 2), (3, 2), (4, 2)}
-HEADERS = ["internal.h", "jet_math.cuh", "mlp_jet_kernels.cuh", "tc_jet_kernels.cuh", "umma.cuh", os.path.join(INCLUDE, "pderead_b200.h")]
+HEADERS = ["internal.h", "jet_math.cuh", "mlp_jet_kernels.cuh", "mlp_plain_kernels.cuh", "tc_jet_kernels.cuh", "umma.cuh", os.path.join(INCLUDE, "pderead_b200.h")]
 
 
 def _newer(target: str, deps) -> bool:

@@ -131,6 +131,18 @@ __global__ void pack_weights_kernel(NetDev net, float* wt, float* wn) {
     }
 }
 
+// plain-MLP forward kernel (mlp_plain_kernels.cuh): wt[l][k][i] = W_{l+1}[i][k], rows padded with zeros to WP
+__global__ void pack_plain_weights_kernel(NetDev net, int WP, float* wt) {
+    const int W = net.W;
+    const size_t per_layer = (size_t)W * WP, total = per_layer * (net.L - 1);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int l = (int)(idx / per_layer);
+        const size_t rem = idx - (size_t)l * per_layer;
+        const int k = (int)(rem / WP), i = (int)(rem - (size_t)k * WP);
+        wt[idx] = (i < W) ? net.w[l + 1][(size_t)i * W + k] : 0.f;
+    }
+}
+
 // dst = beta*dst + scale * sum_over_parts(gpart).  Block = 32 consecutive elements x 8 slices of the partial
 // vectors; every thread sums its slice with four independent accumulators (the loads are the cost), the
 // slices are combined through shared memory in a fixed order, so the result is bit-reproducible.
@@ -660,6 +672,31 @@ static bool tc_allowed(const NetDev& n, bool gradient_path) {
     return !gradient_path && n.W > 64 && n.L >= 3;   // (2 x 100 plain nets measured slower: the output product is half the work)
 }
 
+// Plain-MLP forward kernel (J = 1, register-tiled, weights staged in shared memory): on by default; PDEREAD_PLAIN_MLP=0
+// or pderead_debug_set_plain_mlp(0) selects the lane = point kernel of mlp_jet_kernels.cuh instead (A/B measurements).
+static std::atomic<int> g_plain_mode{-1};
+static int plain_mode() {
+    int m = g_plain_mode.load(std::memory_order_relaxed);
+    if (m < 0) {
+        const char* e = getenv("PDEREAD_PLAIN_MLP");
+        m = (e && (e[0] == '0' || e[0] == 'o' || e[0] == 'O') && !(e[1] == 'n' || e[1] == 'N')) ? 0 : 1;
+        int expect = -1;
+        if (!g_plain_mode.compare_exchange_strong(expect, m)) m = expect;
+    }
+    return m;
+}
+static inline int plain_wp_h(int W) { return (W + 7) / 8 * 8; }
+static bool plain_fits(const NetDev& n, bool stash) {
+    if (!plain_mode() || (n.W + 7) / 8 > 16) return false;
+    int dev = 0, maxsm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
+    const int PP = stash ? 2 : 4, TP = 32 * PP, HS = TP + 4, nw = (n.W + 7) / 8;
+    const size_t smem = sizeof(float) * ((size_t)2 * n.W * HS + (size_t)n.din * TP + (size_t)nw * TP +
+                                         (n.L > 1 ? (size_t)n.W * plain_wp_h(n.W) : 0));
+    return smem + 1024 <= (size_t)maxsm;
+}
+
 static int round_up_i(int v, int a) { return (v + a - 1) / a * a; }
 
 // Picks the tile geometry of the tensor-core kernels for one network and jet length; false if the
@@ -893,7 +930,11 @@ struct Carver {
     }
 };
 
-static size_t packed_floats(const NetDev& n) { return (size_t)(n.L > 1 ? n.L - 1 : 0) * n.W * n.NC * TNP; }
+static size_t packed_floats(const NetDev& n) {
+    const int row = n.NC * TNP > plain_wp_h(n.W) ? n.NC * TNP : plain_wp_h(n.W);     // either weight layout fits
+    return (size_t)(n.L > 1 ? n.L - 1 : 0) * n.W * row;
+}
+static size_t packed_floats_old(const NetDev& n) { return (size_t)(n.L > 1 ? n.L - 1 : 0) * n.W * n.NC * TNP; }
 static size_t stash_floats_per_point(const NetDev& n, int J) { return (size_t)(n.L > 1 ? n.L - 1 : 0) * n.W * J; }
 // bound for the workspace queries: the tensor-core stash keeps 64 / 128 rows per layer
 static size_t stash_floats_bound(const NetDev& n, int J) {
@@ -903,12 +944,33 @@ static size_t stash_floats_bound(const NetDev& n, int J) {
 
 static int pack(const NetDev& n, float* wt, float* wn, cudaStream_t s) {
     if (n.L <= 1 || (!wt && !wn)) return PDEREAD_OK;
-    const size_t total = packed_floats(n);
+    const size_t total = packed_floats_old(n);
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
     pack_weights_kernel<<<blocks, 256, 0, s>>>(n, wt, wn);
     PDR_CUDA_CHECK(cudaGetLastError());
     stage_mark(s, ST_PACK);
     return PDEREAD_OK;
+}
+
+static int pack_plain(const NetDev& n, float* wt, cudaStream_t s) {
+    if (n.L <= 1 || !wt) return PDEREAD_OK;
+    const size_t total = (size_t)(n.L - 1) * n.W * plain_wp_h(n.W);
+    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    pack_plain_weights_kernel<<<blocks, 256, 0, s>>>(n, plain_wp_h(n.W), wt);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark(s, ST_PACK);
+    return PDEREAD_OK;
+}
+
+static int dispatch_plain_fwd(int act, const FwdArgs& a, cudaStream_t s) {
+    int rc = PDEREAD_ERR_UNSUPPORTED_NET;
+    switch (act) {
+        case 0: rc = launch_plain_fwd<0>(a, s); break;
+        case 1: rc = launch_plain_fwd<1>(a, s); break;
+        case 2: rc = launch_plain_fwd<2>(a, s); break;
+    }
+    if (rc == PDEREAD_OK) stage_mark(s, ST_FWD_PLAIN);
+    return rc;
 }
 
 static int reduce_partials(const float* gpart, int nparts, const GradLayout& lay, const SegmentTable& tab, float beta,
@@ -952,6 +1014,7 @@ static int dispatch_tc_bwd(int act, int nx, int nt, const TcBwdArgs& a, int grid
 // A forward launch of one network on whichever path its plan selected.
 struct FwdPlan {
     bool tc;
+    bool plain;   // J = 1: register-tiled kernel with its own weight layout
     TcGeom geom;
     float* wt;    // CUDA-core path: packed transposed weights
     float* img;   // tensor-core path: weight images
@@ -963,6 +1026,7 @@ static int plan_forward(const NetDev& n, int J, bool allow_tc, Carver& cv, FwdPl
     if (p->tc) {
         p->img = cv.take<float>((size_t)n.L * 2 * p->geom.a_bytes / 4);
     } else {
+        p->plain = (J == 1) && plain_fits(n, false);
         p->wt = cv.take<float>(packed_floats(n));
     }
     return cv.ok ? PDEREAD_OK : PDEREAD_ERR_WORKSPACE_TOO_SMALL;
@@ -970,11 +1034,16 @@ static int plan_forward(const NetDev& n, int J, bool allow_tc, Carver& cv, FwdPl
 
 static int plan_pack(const NetDev& n, const FwdPlan& p, cudaStream_t s) {
     if (p.tc) return tc_pack(n, p.geom.mrows, p.geom.Kpad, p.geom.NB, p.geom.a_rs, p.geom.a_bytes, 0, p.img, s);
+    if (p.plain) return pack_plain(n, p.wt, s);
     return pack(n, p.wt, nullptr, s);
 }
 
 // `f` carries everything except wt_packed / num_tiles, which depend on the path.
 static int plan_launch(int act, int nx, int nt, const FwdPlan& p, FwdArgs f, cudaStream_t s) {
+    if (!p.tc && p.plain) {
+        f.wt_packed = p.wt;
+        return dispatch_plain_fwd(act, f, s);
+    }
     if (!p.tc) {
         const int TP = tile_points(jet_len(nx, nt));
         f.wt_packed = p.wt;
@@ -1043,6 +1112,11 @@ int pderead_debug_stage_tags(int32_t* h_tags, int capacity) {
     if (n > capacity) n = capacity;
     for (int i = 0; i < n; ++i) h_tags[i] = g_stage_tags[i];
     return n;
+}
+
+int pderead_debug_set_plain_mlp(int on) {
+    (void)plain_mode();
+    return g_plain_mode.exchange(on ? 1 : 0);
 }
 
 int pderead_debug_set_tensor_cores(int mode) {
@@ -1129,7 +1203,8 @@ static int plan_backward(const NetDev& n, int act, int nx, int nt, bool want_gin
         p->stash_pp = (size_t)(n.L - 1) * J * p->bgeom.mrows;
     } else {
         if ((rc = check_smem(n.W, n.L, n.din, J, true))) return rc;
-        if ((rc = check_smem(n.W, n.L, n.din, J, false))) return rc;
+        p->fwd.plain = (J == 1) && plain_fits(n, true);
+        if (!p->fwd.plain && (rc = check_smem(n.W, n.L, n.din, J, false))) return rc;
         p->fwd.wt = cv.take<float>(packed_floats(n));
         p->wn = cv.take<float>(packed_floats(n));
         const int TP = tile_points(J);
@@ -1147,6 +1222,11 @@ static int plan_backward_pack(const NetDev& n, const BwdPlan& p, cudaStream_t s)
         if ((rc = tc_pack(n, f.mrows, f.Kpad, f.NB, f.a_rs, f.a_bytes, 0, p.fwd.img, s))) return rc;
         const TcBwdGeom& b = p.bgeom;
         return tc_pack(n, b.mrows, b.Kpad, b.NB, b.a_rs, b.a_bytes, 1, p.timg, s);
+    }
+    if (p.fwd.plain) {
+        int rc = pack_plain(n, p.fwd.wt, s);
+        if (rc) return rc;
+        return pack(n, nullptr, p.wn, s);
     }
     return pack(n, p.fwd.wt, p.wn, s);
 }
@@ -1303,7 +1383,7 @@ int pderead_mlp_forward(const pderead_net* net, const float* d_in, int64_t M, fl
     Carver cv(ws, ws_bytes);
     FwdPlan pl;
     if ((rc = plan_forward(N, 1, true, cv, &pl))) return rc;
-    if (!pl.tc && (rc = check_smem(N.W, N.L, N.din, 1, false))) return rc;
+    if (!pl.tc && !pl.plain && (rc = check_smem(N.W, N.L, N.din, 1, false))) return rc;
     if (!ws && (pl.tc || packed_floats(N))) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
     if ((rc = plan_pack(N, pl, s))) return rc;
     FwdArgs a;
@@ -1383,7 +1463,7 @@ static int residual_impl(const pderead_net* sol, const pderead_net* pde, int m, 
         if ((rc = plan_forward(U, J, true, cv, &fU))) return rc;
         if ((rc = plan_forward(N, 1, true, cv, &fN))) return rc;
         if (!fU.tc && (rc = check_smem(U.W, U.L, U.din, J, false))) return rc;
-        if (!fN.tc && (rc = check_smem(N.W, N.L, N.din, 1, false))) return rc;
+        if (!fN.tc && !fN.plain && (rc = check_smem(N.W, N.L, N.din, 1, false))) return rc;
     }
     if (!cv.ok) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
     size_t per_point = (size_t)(n + 2) * 4;
@@ -1521,7 +1601,7 @@ int pderead_extraction_gram(const pderead_net* sol, const pderead_net* pde, int 
     if ((rc = plan_forward(U, J, true, cv, &plU))) return rc;
     if ((rc = plan_forward(N, 1, true, cv, &plN))) return rc;
     if (!plU.tc && (rc = check_smem(U.W, U.L, U.din, J, false))) return rc;
-    if (!plN.tc && (rc = check_smem(N.W, N.L, N.din, 1, false))) return rc;
+    if (!plN.tc && !plN.plain && (rc = check_smem(N.W, N.L, N.din, 1, false))) return rc;
     const size_t per_point = (size_t)(n + 2) * 4;
     const size_t remain = ws_bytes - cv.used;
     long long chunk = (long long)((remain > 4096 ? remain - 4096 : 0) / per_point);

@@ -77,6 +77,7 @@ struct FwdArgs {
     const float* grad_resid;  // optional externally supplied dL/dR (then seed_out = -grad_resid)
     float seed_scale;
     double* sumsq;
+    int aux;                  // mlp_plain_fwd_kernel: number of weight buffers in shared memory
 };
 
 struct BwdArgs {
@@ -188,6 +189,9 @@ template <int ACT, int NX, int NT>
 int bwd_grid(int W, int L, int din, long long num_tiles, int* grid_out);
 template <int ACT, int NX, int NT>
 int launch_bwd_impl(const BwdArgs& a, int grid, cudaStream_t stream);
+
+template <int ACT>
+int launch_plain_fwd(const FwdArgs& a, cudaStream_t stream);   // register-tiled plain MLP (J = 1), mlp_plain_kernels.cuh
 
 template <int ACT, int NX, int NT>
 int launch_tc_fwd(const TcFwdArgs& a, cudaStream_t stream);

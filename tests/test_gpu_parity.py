@@ -102,8 +102,17 @@ def test_random_nets_match_reference_golden(path):
     assert abs(loss.item() - float(z["loss"])) <= 2e-5 * abs(float(z["loss"]))
     loss.backward()
     for pref, net in (("gsol.", U), ("gpde.", N)):
+        gmax = max(float(np.abs(z[pref + k]).max()) for k, _ in net.named_parameters())
         for k, g in grads_of(net).items():
-            assert_close_to_reference(g, z[pref + k], z[pref + k + ".f64"], TOL_GRAD, name + " " + pref + k)
+            ref = z[pref + k]
+            if float(np.abs(ref).max()) < 1e-2 * gmax:
+                # a tensor that is a near-cancelling sum (e.g. the one-element output bias of a network whose mean
+                # residual is ~1e-4 of its terms): its own maximum is no scale -- the float32 reference is itself only
+                # good to ~1e-7 of the TERMS.  Compare on the scale of the network's gradient instead.
+                # (here: ours 5.2106e-4, float32 reference 5.2092e-4, float64 reference 5.2067e-4, largest entry 1.43)
+                assert np.abs(g - ref).max() <= TOL_GRAD * 1e-2 * gmax, (name, pref + k, g, ref, z[pref + k + ".f64"])
+            else:
+                assert_close_to_reference(g, ref, z[pref + k + ".f64"], TOL_GRAD, name + " " + pref + k)
 
 
 def test_residual_autograd_matches_loss_autograd():
