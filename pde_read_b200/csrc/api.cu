@@ -132,14 +132,17 @@ __global__ void pack_weights_kernel(NetDev net, float* wt, float* wn) {
 }
 
 // plain-MLP forward kernel (mlp_plain_kernels.cuh): wt[l][k][i] = W_{l+1}[i][k], rows padded with zeros to WP
-__global__ void pack_plain_weights_kernel(NetDev net, int WP, float* wt) {
+// (native != 0: wn[l][i][k] = W_{l+1}[i][k], the layout of the plain reverse kernel)
+__global__ void pack_plain_weights_kernel(NetDev net, int WP, int native, float* wt) {
     const int W = net.W;
     const size_t per_layer = (size_t)W * WP, total = per_layer * (net.L - 1);
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int l = (int)(idx / per_layer);
         const size_t rem = idx - (size_t)l * per_layer;
-        const int k = (int)(rem / WP), i = (int)(rem - (size_t)k * WP);
-        wt[idx] = (i < W) ? net.w[l + 1][(size_t)i * W + k] : 0.f;
+        const int r = (int)(rem / WP), c = (int)(rem - (size_t)r * WP);
+        float v = 0.f;
+        if (c < W) v = native ? net.w[l + 1][(size_t)r * W + c] : net.w[l + 1][(size_t)c * W + r];
+        wt[idx] = v;
     }
 }
 
@@ -952,11 +955,11 @@ static int pack(const NetDev& n, float* wt, float* wn, cudaStream_t s) {
     return PDEREAD_OK;
 }
 
-static int pack_plain(const NetDev& n, float* wt, cudaStream_t s) {
+static int pack_plain(const NetDev& n, float* wt, cudaStream_t s, int native = 0) {
     if (n.L <= 1 || !wt) return PDEREAD_OK;
     const size_t total = (size_t)(n.L - 1) * n.W * plain_wp_h(n.W);
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    pack_plain_weights_kernel<<<blocks, 256, 0, s>>>(n, plain_wp_h(n.W), wt);
+    pack_plain_weights_kernel<<<blocks, 256, 0, s>>>(n, plain_wp_h(n.W), native, wt);
     PDR_CUDA_CHECK(cudaGetLastError());
     stage_mark(s, ST_PACK);
     return PDEREAD_OK;
@@ -970,6 +973,38 @@ static int dispatch_plain_fwd(int act, const FwdArgs& a, cudaStream_t s) {
         case 2: rc = launch_plain_fwd<2>(a, s); break;
     }
     if (rc == PDEREAD_OK) stage_mark(s, ST_FWD_PLAIN);
+    return rc;
+}
+
+static bool plain_bwd_fits(const NetDev& n) {
+    if (!plain_mode() || (n.W + 7) / 8 > 16) return false;
+    int dev = 0, maxsm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
+    const int TP = 128, HS = TP + 4;
+    const size_t ns = (((size_t)n.L * n.W + 1 + (size_t)n.W * n.din + n.W + 7 * n.L + 3) & ~(size_t)3) + HS;
+    const size_t smem = sizeof(float) * ((size_t)2 * n.W * HS + (size_t)2 * n.din * TP + TP + ns +
+                                         (n.L > 1 ? (size_t)n.W * plain_wp_h(n.W) : 0));
+    return smem + 1024 <= (size_t)maxsm;
+}
+
+static int dispatch_plain_bwd_grid(int act, int W, int L, int din, long long tiles, int* grid) {
+    switch (act) {
+        case 0: return plain_bwd_grid<0>(W, L, din, tiles, grid);
+        case 1: return plain_bwd_grid<1>(W, L, din, tiles, grid);
+        case 2: return plain_bwd_grid<2>(W, L, din, tiles, grid);
+    }
+    return PDEREAD_ERR_UNSUPPORTED_NET;
+}
+
+static int dispatch_plain_bwd(int act, const BwdArgs& a, int grid, cudaStream_t s) {
+    int rc = PDEREAD_ERR_UNSUPPORTED_NET;
+    switch (act) {
+        case 0: rc = launch_plain_bwd<0>(a, grid, s); break;
+        case 1: rc = launch_plain_bwd<1>(a, grid, s); break;
+        case 2: rc = launch_plain_bwd<2>(a, grid, s); break;
+    }
+    if (rc == PDEREAD_OK) stage_mark(s, ST_BWD_PLAIN);
     return rc;
 }
 
@@ -1015,6 +1050,7 @@ static int dispatch_tc_bwd(int act, int nx, int nt, const TcBwdArgs& a, int grid
 struct FwdPlan {
     bool tc;
     bool plain;   // J = 1: register-tiled kernel with its own weight layout
+    int stash_pp; // plain kernel with a stash: points per lane of the stash tile (2 or 4)
     TcGeom geom;
     float* wt;    // CUDA-core path: packed transposed weights
     float* img;   // tensor-core path: weight images
@@ -1042,6 +1078,7 @@ static int plan_pack(const NetDev& n, const FwdPlan& p, cudaStream_t s) {
 static int plan_launch(int act, int nx, int nt, const FwdPlan& p, FwdArgs f, cudaStream_t s) {
     if (!p.tc && p.plain) {
         f.wt_packed = p.wt;
+        f.aux2 = p.stash_pp;
         return dispatch_plain_fwd(act, f, s);
     }
     if (!p.tc) {
@@ -1176,6 +1213,7 @@ int pderead_sol_derivatives_forward(const pderead_net* sol, int m, int n, const 
 // ---------------------------------------------------------------------------------------------
 struct BwdPlan {
     bool tc;
+    bool plain;     // J = 1: register-tiled reverse kernel (tile of 128 points)
     FwdPlan fwd;
     TcBwdGeom bgeom;
     float* wn;      // CUDA-core path: native packed weights
@@ -1202,13 +1240,21 @@ static int plan_backward(const NetDev& n, int act, int nx, int nt, bool want_gin
         p->grid = (int)(tiles < sms ? tiles : sms);
         p->stash_pp = (size_t)(n.L - 1) * J * p->bgeom.mrows;
     } else {
-        if ((rc = check_smem(n.W, n.L, n.din, J, true))) return rc;
-        p->fwd.plain = (J == 1) && plain_fits(n, true);
+        // (128-point tiles need enough points to fill the GPU: below ~100 tiles per 148 SMs the 64-point kernel wins,
+        //  C1's 5000 points: 0.063 vs 0.081 ms)
+        p->plain = (J == 1) && M >= 16384 && plain_bwd_fits(n) && plain_fits(n, false);
+        if (!p->plain && (rc = check_smem(n.W, n.L, n.din, J, true))) return rc;
+        p->fwd.plain = p->plain || ((J == 1) && plain_fits(n, true));
+        p->fwd.stash_pp = p->plain ? 4 : 2;
         if (!p->fwd.plain && (rc = check_smem(n.W, n.L, n.din, J, false))) return rc;
         p->fwd.wt = cv.take<float>(packed_floats(n));
         p->wn = cv.take<float>(packed_floats(n));
-        const int TP = tile_points(J);
-        if ((rc = dispatch_bwd_grid(act, nx, nt, n.W, n.L, n.din, (M + TP - 1) / TP, &p->grid))) return rc;
+        if (p->plain) {
+            if ((rc = dispatch_plain_bwd_grid(act, n.W, n.L, n.din, (M + 127) / 128, &p->grid))) return rc;
+        } else {
+            const int TP = tile_points(J);
+            if ((rc = dispatch_bwd_grid(act, nx, nt, n.W, n.L, n.din, (M + TP - 1) / TP, &p->grid))) return rc;
+        }
         p->stash_pp = stash_floats_per_point(n, J);
     }
     p->gpart = cv.take<float>((size_t)p->grid * lay.total);
@@ -1226,7 +1272,7 @@ static int plan_backward_pack(const NetDev& n, const BwdPlan& p, cudaStream_t s)
     if (p.fwd.plain) {
         int rc = pack_plain(n, p.fwd.wt, s);
         if (rc) return rc;
-        return pack(n, nullptr, p.wn, s);
+        return p.plain ? pack_plain(n, p.wn, s, 1) : pack(n, nullptr, p.wn, s);
     }
     return pack(n, p.fwd.wt, p.wn, s);
 }
@@ -1258,14 +1304,15 @@ static int plan_backward_launch(int act, int nx, int nt, BwdPlan& p, BwdArgs b, 
         if (first) p.grid = g;      // later chunks are never larger than the first
         return dispatch_tc_bwd(act, nx, nt, t, g, s);
     }
-    const int TP = tile_points(jet_len(nx, nt));
+    const int TP = p.plain ? 128 : tile_points(jet_len(nx, nt));
     b.wn_packed = p.wn;
     b.num_tiles = (b.M + TP - 1) / TP;
     {
         // weight-gradient tiling: a warp owns 10 x (16 TK) outputs, TK in {2, 3, 4}; take the one with the fewest
         // (rounds x outputs per thread) over W x (W + 1 bias column); ties go to the larger tile (fewer
         // shared-memory wavefronts per FMA)
-        const int nw = bwd_block_warps(b.net.W, b.net.L, b.net.din, jet_len(nx, nt)), W = b.net.W;
+        const int W = b.net.W;
+        const int nw = p.plain ? (W + 7) / 8 : bwd_block_warps(b.net.W, b.net.L, b.net.din, jet_len(nx, nt));
         long best = -1;
         for (int m = 2; m >= 0; --m) {
             const int tk = 2 + m;
@@ -1280,6 +1327,7 @@ static int plan_backward_launch(int act, int nx, int nt, BwdPlan& p, BwdArgs b, 
     int g = p.grid;
     if (b.num_tiles < g) g = (int)b.num_tiles;
     if (first) p.grid = g;
+    if (p.plain) return dispatch_plain_bwd(act, b, g, s);
     return dispatch_bwd(act, nx, nt, b, g, s);
 }
 

@@ -9,6 +9,8 @@ namespace pdr {
 template int launch_fwd<PDR_ACT, PDR_NX, PDR_NT>(const FwdArgs&, cudaStream_t);
 #if PDR_NX == 0 && PDR_NT == 0
 template int launch_plain_fwd<PDR_ACT>(const FwdArgs&, cudaStream_t);
+template int plain_bwd_grid<PDR_ACT>(int, int, int, long long, int*);
+template int launch_plain_bwd<PDR_ACT>(const BwdArgs&, int, cudaStream_t);
 #endif
 template int launch_tc_fwd<PDR_ACT, PDR_NX, PDR_NT>(const TcFwdArgs&, cudaStream_t);
 #if PDR_BWD

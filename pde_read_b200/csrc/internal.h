@@ -78,6 +78,7 @@ struct FwdArgs {
     float seed_scale;
     double* sumsq;
     int aux;                  // mlp_plain_fwd_kernel: number of weight buffers in shared memory
+    int aux2;                 // mlp_plain_fwd_kernel with a stash: points per lane of the stash tile (2: 64 points, 4: 128)
 };
 
 struct BwdArgs {
@@ -95,6 +96,7 @@ struct BwdArgs {
     float* gpart;             // [gridDim.x][lay.total]
     int wg_mode;
     int accumulate;           // 0: this launch zeroes its partial-gradient vectors first
+    int aux;                  // mlp_plain_bwd_kernel: number of weight buffers in shared memory
 };
 
 // ---- tensor-core path (tc_jet_kernels.cuh) ----------------------------------------------------
@@ -192,6 +194,10 @@ int launch_bwd_impl(const BwdArgs& a, int grid, cudaStream_t stream);
 
 template <int ACT>
 int launch_plain_fwd(const FwdArgs& a, cudaStream_t stream);   // register-tiled plain MLP (J = 1), mlp_plain_kernels.cuh
+template <int ACT>
+int plain_bwd_grid(int W, int L, int din, long long num_tiles, int* grid_out);
+template <int ACT>
+int launch_plain_bwd(const BwdArgs& a, int grid, cudaStream_t stream);
 
 template <int ACT, int NX, int NT>
 int launch_tc_fwd(const TcFwdArgs& a, cudaStream_t stream);
