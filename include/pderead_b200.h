@@ -247,11 +247,11 @@ int pderead_debug_stage_tags(int32_t* h_tags, int capacity);
  * layer's weights staged in shared memory (on, default) or the lane = point kernel (off; also PDEREAD_PLAIN_MLP=0).
  * A measurement switch; both produce the same numbers up to summation order.  Returns the previous setting. */
 int pderead_debug_set_plain_mlp(int on);
-/* Tensor-core policy for the hidden-layer products (tcgen05, 3xTF32; widths 8..128, depth >= 2):
+/* Tensor-core policy of the forward-only jet calls (tcgen05, 3xTF32; widths 8..128, depth >= 2):
  *   0 off   - CUDA-core kernels everywhere;
- *   1 auto  - default: forward-only calls of networks wider than 64 (>= 3 hidden layers) use the tensor cores, the gradient
- *             path stays on the CUDA cores (fp32-exact accumulation);
- *   2 force - tensor cores wherever the shape is supported, including the reverse pass.
+ *   1 auto  - default: forward-only calls of networks wider than 64 (>= 3 hidden layers) use the tensor cores;
+ *   2 force - the tensor-core forward for every forward-only call whose shape it supports.
+ * The gradient path (forward with stash + reverse) always runs on the CUDA cores (fp32-exact accumulation).
  * Also selectable with the environment variable PDEREAD_TC=off|auto|force.  Returns the previous mode. */
 int pderead_debug_set_tensor_cores(int mode);
 

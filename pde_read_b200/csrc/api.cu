@@ -184,13 +184,13 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 // One image per product gi = 1..L of a network: [hi | lo], each MROWS x Kpad fp32, K-major core-matrix
 // layout (8 rows x 16 bytes contiguous; LBO = 128 between 4-k groups, SBO = a_rs between 8-row groups).
 // Row r of image gi < L holds the weights of neuron nid(r) of hidden layer gi (zero for unused rows);
-// image L holds the output layer's weights in row 0.  transpose != 0 packs W^T (for hbar = W^T zbar).
-__global__ void tc_pack_weights_kernel(NetDev net, int mrows, int Kpad, int NB, int a_rs, int a_bytes, int transpose,
+// image L holds the output layer's weights in row 0.
+__global__ void tc_pack_weights_kernel(NetDev net, int mrows, int Kpad, int NB, int a_rs, int a_bytes,
                                        float* __restrict__ img) {
     const int W = net.W, L = net.L;
     const size_t per_img = (size_t)2 * a_bytes / 4;   // floats
     const int per_mat = mrows * Kpad;
-    const int nimg = L;   // forward: L-1 hidden + output row; transposed: L-1 hidden + input layer (for the input gradient)
+    const int nimg = L;   // L-1 hidden products + the output row
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)nimg * per_mat;
          idx += (size_t)gridDim.x * blockDim.x) {
         const int gi = (int)(idx / per_mat) + 1;
@@ -202,11 +202,9 @@ __global__ void tc_pack_weights_kernel(NetDev net, int mrows, int Kpad, int NB, 
         float v = 0.f;
         if (k < W) {
             if (gi < L) {
-                if (rl < NB && nid < W) v = transpose ? net.w[gi][(size_t)k * W + nid] : net.w[gi][(size_t)nid * W + k];
-            } else if (!transpose) {
-                if (r == 0) v = net.w[L][k];
+                if (rl < NB && nid < W) v = net.w[gi][(size_t)nid * W + k];
             } else {
-                if (r < net.din) v = net.w[0][(size_t)k * net.din + r];
+                if (r == 0) v = net.w[L][k];
             }
         }
         const size_t off = ((size_t)(r & 7) * 16 + (size_t)(r >> 3) * a_rs + (size_t)(k & 3) * 4 + (size_t)(k >> 2) * 128) / 4;
@@ -649,12 +647,13 @@ static bool order_supported(int nx, int nt) {
 // ---------------------------------------------------------------------------------------------
 // tensor-core path: geometry, weight images, dispatch
 // ---------------------------------------------------------------------------------------------
-// Tensor-core policy.  0 = off: CUDA-core kernels everywhere.  1 = auto (default): forward-only calls of
-// networks wider than 64 with at least 3 hidden layers run on the tensor cores (measured 1.6-2x faster there, and inside the stated
-// derivative / residual tolerances); everything on the gradient path stays on the CUDA cores, because the
-// tensor core truncates inside its accumulation and 3xTF32 lands at ~1e-6 relative error per network
-// instead of fp32's ~1e-7, which the residual cancellation of a trained network amplifies in the
-// gradients.  2 = force: tensor cores wherever the shape is supported.
+// Tensor-core policy (forward kernel only).  0 = off: CUDA-core kernels everywhere.  1 = auto (default): forward-only
+// jet calls (Evaluate_Derivatives, PDE_Residual without grad, extraction) of networks wider than 64 with at least 3
+// hidden layers run on the tensor cores (measured 1.5x faster at width 100, inside the stated derivative / residual
+// tolerances).  Everything on the gradient path stays on the CUDA cores: the tensor core truncates inside its
+// accumulation and 3xTF32 lands at ~1e-6 relative error per network instead of fp32's ~1e-7, which the residual
+// cancellation of a trained network amplifies in the gradients.  2 = force: the tensor-core forward for
+// every forward-only call whose shape it supports (tests, measurements).
 static std::atomic<int> g_tc_mode{-1};
 static int tc_mode() {
     int m = g_tc_mode.load(std::memory_order_relaxed);
@@ -670,9 +669,9 @@ static int tc_mode() {
 }
 static bool tc_allowed(const NetDev& n, bool gradient_path) {
     const int m = tc_mode();
-    if (m == 0) return false;
+    if (m == 0 || gradient_path) return false;       // there is no tensor-core reverse kernel (removed in round 2)
     if (m == 2) return true;
-    return !gradient_path && n.W > 64 && n.L >= 3;   // (2 x 100 plain nets measured slower: the output product is half the work)
+    return n.W > 64 && n.L >= 3;   // (2 x 100 plain nets measured slower: the output product is half the work)
 }
 
 // Plain-MLP forward kernel (J = 1, register-tiled, weights staged in shared memory): on by default; PDEREAD_PLAIN_MLP=0
@@ -756,83 +755,13 @@ static size_t tc_image_bytes_bound(const NetDev& n) {
     return (size_t)n.L * 2 * 16 * (size_t)(round_up_i(n.W, 8) / 4) * 128;
 }
 
-static int tc_pack(const NetDev& n, int mrows, int Kpad, int NB, int a_rs, int a_bytes, int transpose, float* img,
-                   cudaStream_t s) {
+static int tc_pack(const NetDev& n, int mrows, int Kpad, int NB, int a_rs, int a_bytes, float* img, cudaStream_t s) {
     const size_t total = (size_t)n.L * mrows * Kpad;
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    tc_pack_weights_kernel<<<blocks, 256, 0, s>>>(n, mrows, Kpad, NB, a_rs, a_bytes, transpose, img);
+    tc_pack_weights_kernel<<<blocks, 256, 0, s>>>(n, mrows, Kpad, NB, a_rs, a_bytes, img);
     PDR_CUDA_CHECK(cudaGetLastError());
     stage_mark(s, ST_PACK);
     return PDEREAD_OK;
-}
-
-static int jet_cols(int J) { return (J == 3) ? 4 : (J == 5) ? 6 : (J == 7) ? 8 : J; }
-
-// Geometry of the tensor-core reverse kernel; false -> CUDA-core kernels.
-static bool tc_bwd_geometry(const NetDev& n, int J, bool want_gin, TcBwdGeom* g) {
-    if (!tc_allowed(n, true)) return false;
-    if (n.L < 2 || n.W < 8 || n.W > 128 || J < 1 || J > 7) return false;
-    if (want_gin && J != 1) return false;
-    int dev = 0, maxsm = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return false;
-    if (cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
-    memset(g, 0, sizeof(*g));
-    g->mrows = (n.W <= 64) ? 64 : 128;
-    const int subs = (g->mrows == 64) ? 2 : 1;
-    const int gran = (g->mrows == 128) ? 16 : 8;
-    g->Kpad = round_up_i(n.W, 8);
-    g->NB = (n.W + 3) / 4;
-    g->Jp = jet_cols(J);
-    const int G = (g->Jp == 1) ? 8 : (g->Jp == 2) ? 4 : 2;
-    g->a_rs = (g->Kpad / 4) * 128;
-    g->a_bytes = (g->mrows / 8) * g->a_rs;
-    g->zt_rs = (g->Kpad / 4) * 144;
-    g->npad_w = round_up_i(g->Kpad, gran);
-    const int NS = n.L * n.W + 1 + n.W * n.din + n.W + 7 * n.L;
-    const int pcs_jet[] = {16, 8, 4, 0}, pcs_plain[] = {64, 32, 16, 0};
-    const int* pcs = (J == 1) ? pcs_plain : pcs_jet;
-    for (int nchunk = 2; nchunk >= 1; --nchunk) {
-        for (int t = 0; pcs[t]; ++t) {
-            for (int nwbuf = 2; nwbuf >= 1; --nwbuf) {
-                const int PC = pcs[t];
-                if ((PC / 2) % G != 0) continue;
-                const int NC = PC * g->Jp;
-                if (NC % 8 != 0) continue;
-                const int ncpad = round_up_i(NC, gran);
-                if (ncpad > 256) continue;
-                const int tmem = 2 * nchunk * ncpad + (n.L - 1) * g->npad_w;   // hbar: main + correction accumulators
-                if (tmem > 512) continue;
-                const int za_rs = (NC / 4) * 128;
-                const int za_bytes = (g->mrows / 8) * za_rs, yb_bytes = (g->npad_w / 8) * za_rs;
-                const int zt_bytes = (ncpad / 8) * g->zt_rs;
-                const int set_bytes = 2 * (zt_bytes + za_bytes + yb_bytes);
-                const int sub_stride = nchunk * set_bytes + 64;
-                const int TP = subs * nchunk * PC;
-                const size_t smem = (size_t)nwbuf * 2 * g->a_bytes + (size_t)subs * sub_stride +
-                                    (size_t)(n.din * TP + J * TP + ((NS + 1) & ~1)) * 4 + 9 * 8 + 64;
-                if (smem > (size_t)maxsm) continue;
-                g->PC = PC;
-                g->nchunk = nchunk;
-                g->NC = NC;
-                g->NCpad = ncpad;
-                g->TP = TP;
-                g->zt_bytes = zt_bytes;
-                g->za_bytes = za_bytes;
-                g->za_rs = za_rs;
-                g->yb_bytes = yb_bytes;
-                g->set_bytes = set_bytes;
-                g->sub_stride = sub_stride;
-                g->nwbuf = nwbuf;
-                g->gcol0 = 2 * nchunk * ncpad;
-                int cols = 32;
-                while (cols < tmem) cols <<= 1;
-                g->tmem_cols = cols;
-                g->smem_bytes = smem;
-                return true;
-            }
-        }
-    }
-    return false;
 }
 
 #define PDR_FWD_COMBOS(X) X(0, 0) X(1, 0) X(2, 0) X(3, 0) X(4, 0) X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(1, 2) X(2, 2) X(3, 2) X(4, 2)
@@ -939,11 +868,7 @@ static size_t packed_floats(const NetDev& n) {
 }
 static size_t packed_floats_old(const NetDev& n) { return (size_t)(n.L > 1 ? n.L - 1 : 0) * n.W * n.NC * TNP; }
 static size_t stash_floats_per_point(const NetDev& n, int J) { return (size_t)(n.L > 1 ? n.L - 1 : 0) * n.W * J; }
-// bound for the workspace queries: the tensor-core stash keeps 64 / 128 rows per layer
-static size_t stash_floats_bound(const NetDev& n, int J) {
-    const size_t rows = (n.W <= 64) ? 64 : (n.W <= 128 ? 128 : (size_t)n.W);
-    return (size_t)(n.L > 1 ? n.L - 1 : 0) * rows * J;
-}
+static size_t stash_floats_bound(const NetDev& n, int J) { return stash_floats_per_point(n, J); }
 
 static int pack(const NetDev& n, float* wt, float* wn, cudaStream_t s) {
     if (n.L <= 1 || (!wt && !wn)) return PDEREAD_OK;
@@ -1032,20 +957,6 @@ static int dispatch_tc_fwd(int act, int nx, int nt, const TcFwdArgs& a, cudaStre
     return PDEREAD_ERR_UNSUPPORTED_ORDER;
 }
 
-static int dispatch_tc_bwd(int act, int nx, int nt, const TcBwdArgs& a, int grid, cudaStream_t s) {
-#define CASE(X_, T_)                                                   \
-    if (nx == X_ && nt == T_) {                                        \
-        switch (act) {                                                 \
-            case 0: { const int rc = launch_tc_bwd<0, X_, T_>(a, grid, s); if (rc == PDEREAD_OK) stage_mark(s, (X_ + T_) ? ST_BWD_JET : ST_BWD_PLAIN); return rc; } \
-            case 1: { const int rc = launch_tc_bwd<1, X_, T_>(a, grid, s); if (rc == PDEREAD_OK) stage_mark(s, (X_ + T_) ? ST_BWD_JET : ST_BWD_PLAIN); return rc; } \
-            case 2: { const int rc = launch_tc_bwd<2, X_, T_>(a, grid, s); if (rc == PDEREAD_OK) stage_mark(s, (X_ + T_) ? ST_BWD_JET : ST_BWD_PLAIN); return rc; } \
-        }                                                              \
-    }
-    PDR_BWD_COMBOS(CASE)
-#undef CASE
-    return PDEREAD_ERR_UNSUPPORTED_ORDER;
-}
-
 // A forward launch of one network on whichever path its plan selected.
 struct FwdPlan {
     bool tc;
@@ -1058,7 +969,9 @@ struct FwdPlan {
 
 static int plan_forward(const NetDev& n, int J, bool allow_tc, Carver& cv, FwdPlan* p) {
     memset(p, 0, sizeof(*p));
-    p->tc = allow_tc && tc_geometry(n, J, false, &p->geom);
+    // J = 1: the register-tiled plain-MLP kernel beats the tensor-core forward (5 x 100: 4.7 vs 6.0 ms per 2 M points)
+    const bool prefer_plain = (J == 1) && tc_mode() != 2 && plain_fits(n, false);
+    p->tc = allow_tc && !prefer_plain && tc_geometry(n, J, false, &p->geom);
     if (p->tc) {
         p->img = cv.take<float>((size_t)n.L * 2 * p->geom.a_bytes / 4);
     } else {
@@ -1069,7 +982,7 @@ static int plan_forward(const NetDev& n, int J, bool allow_tc, Carver& cv, FwdPl
 }
 
 static int plan_pack(const NetDev& n, const FwdPlan& p, cudaStream_t s) {
-    if (p.tc) return tc_pack(n, p.geom.mrows, p.geom.Kpad, p.geom.NB, p.geom.a_rs, p.geom.a_bytes, 0, p.img, s);
+    if (p.tc) return tc_pack(n, p.geom.mrows, p.geom.Kpad, p.geom.NB, p.geom.a_rs, p.geom.a_bytes, p.img, s);
     if (p.plain) return pack_plain(n, p.wt, s);
     return pack(n, p.wt, nullptr, s);
 }
@@ -1097,7 +1010,6 @@ static int plan_launch(int act, int nx, int nt, const FwdPlan& p, FwdArgs f, cud
     t.num_tiles = (f.M + p.geom.TP - 1) / p.geom.TP;
     t.out0 = f.out0;
     t.out1 = f.out1;
-    t.stash = f.stash;
     t.dtm_in = f.dtm_in;
     t.resid_out = f.resid_out;
     t.seed_out = f.seed_out;
@@ -1169,7 +1081,7 @@ size_t pderead_sol_derivatives_workspace_bytes(const pderead_net* sol, int m, in
     if (to_netdev(sol, &U) != PDEREAD_OK || M < 0) return 0;
     const int J = jet_len(n, m);
     size_t bytes = align_up(packed_floats(U) * 4, 256) * (need_backward ? 2 : 1);
-    bytes += align_up(tc_image_bytes_bound(U), 256) * (need_backward ? 2 : 1);
+    bytes += align_up(tc_image_bytes_bound(U), 256);
     if (need_backward) {
         const GradLayout lay = make_layout(U);
         bytes += align_up((size_t)max_grid(U, J) * lay.total * 4, 256);
@@ -1212,12 +1124,9 @@ int pderead_sol_derivatives_forward(const pderead_net* sol, int m, int n, const 
 // is supported, the CUDA-core kernels otherwise
 // ---------------------------------------------------------------------------------------------
 struct BwdPlan {
-    bool tc;
     bool plain;     // J = 1: register-tiled reverse kernel (tile of 128 points)
     FwdPlan fwd;
-    TcBwdGeom bgeom;
-    float* wn;      // CUDA-core path: native packed weights
-    float* timg;    // tensor-core path: transposed weight images
+    float* wn;      // native packed weights
     int grid;       // CTAs of the reverse kernel = number of partial-gradient vectors
     float* gpart;
     size_t stash_pp;   // stash floats per point
@@ -1228,18 +1137,8 @@ static int plan_backward(const NetDev& n, int act, int nx, int nt, bool want_gin
     int rc;
     const int J = jet_len(nx, nt);
     memset(p, 0, sizeof(*p));
-    p->tc = tc_geometry(n, J, true, &p->fwd.geom) && tc_bwd_geometry(n, J, want_gin, &p->bgeom);
-    p->fwd.tc = p->tc;
-    if (p->tc) {
-        int dev = 0, sms = 0;
-        PDR_CUDA_CHECK(cudaGetDevice(&dev));
-        PDR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        p->fwd.img = cv.take<float>((size_t)n.L * 2 * p->fwd.geom.a_bytes / 4);
-        p->timg = cv.take<float>((size_t)n.L * 2 * p->bgeom.a_bytes / 4);
-        const long long tiles = (M + p->bgeom.TP - 1) / p->bgeom.TP;
-        p->grid = (int)(tiles < sms ? tiles : sms);
-        p->stash_pp = (size_t)(n.L - 1) * J * p->bgeom.mrows;
-    } else {
+    (void)want_gin;
+    {
         // (128-point tiles need enough points to fill the GPU: below ~100 tiles per 148 SMs the 64-point kernel wins,
         //  C1's 5000 points: 0.063 vs 0.081 ms)
         p->plain = (J == 1) && M >= 16384 && plain_bwd_fits(n) && plain_fits(n, false);
@@ -1262,13 +1161,6 @@ static int plan_backward(const NetDev& n, int act, int nx, int nt, bool want_gin
 }
 
 static int plan_backward_pack(const NetDev& n, const BwdPlan& p, cudaStream_t s) {
-    int rc;
-    if (p.tc) {
-        const TcGeom& f = p.fwd.geom;
-        if ((rc = tc_pack(n, f.mrows, f.Kpad, f.NB, f.a_rs, f.a_bytes, 0, p.fwd.img, s))) return rc;
-        const TcBwdGeom& b = p.bgeom;
-        return tc_pack(n, b.mrows, b.Kpad, b.NB, b.a_rs, b.a_bytes, 1, p.timg, s);
-    }
     if (p.fwd.plain) {
         int rc = pack_plain(n, p.fwd.wt, s);
         if (rc) return rc;
@@ -1281,29 +1173,6 @@ static int plan_backward_pack(const NetDev& n, const BwdPlan& p, cudaStream_t s)
 static int plan_backward_launch(int act, int nx, int nt, BwdPlan& p, BwdArgs b, bool first, cudaStream_t s) {
     b.accumulate = first ? 0 : 1;
     b.gpart = p.gpart;
-    if (p.tc) {
-        TcBwdArgs t;
-        memset(&t, 0, sizeof(t));
-        t.net = b.net;
-        t.lay = b.lay;
-        t.geom = p.bgeom;
-        t.wimg = p.timg;
-        t.in = b.in;
-        t.M = b.M;
-        t.num_tiles = (b.M + p.bgeom.TP - 1) / p.bgeom.TP;
-        t.stash = b.stash;
-        t.g0 = b.g0;
-        t.g1 = b.g1;
-        t.g0_scale = b.g0_scale;
-        t.g1_scale = b.g1_scale;
-        t.gin = b.gin;
-        t.gpart = p.gpart;
-        t.accumulate = b.accumulate;
-        int g = p.grid;
-        if (t.num_tiles < g) g = (int)t.num_tiles;
-        if (first) p.grid = g;      // later chunks are never larger than the first
-        return dispatch_tc_bwd(act, nx, nt, t, g, s);
-    }
     const int TP = p.plain ? 128 : tile_points(jet_len(nx, nt));
     b.wn_packed = p.wn;
     b.num_tiles = (b.M + TP - 1) / TP;
@@ -1409,7 +1278,7 @@ size_t pderead_mlp_workspace_bytes(const pderead_net* net, int64_t M, int need_b
     NetDev N;
     if (to_netdev(net, &N) != PDEREAD_OK || M < 0) return 0;
     size_t bytes = align_up(packed_floats(N) * 4, 256) * (need_backward ? 2 : 1);
-    bytes += align_up(tc_image_bytes_bound(N), 256) * (need_backward ? 2 : 1);
+    bytes += align_up(tc_image_bytes_bound(N), 256);
     if (need_backward) {
         const GradLayout lay = make_layout(N);
         bytes += align_up((size_t)max_grid(N, 1) * lay.total * 4, 256);
@@ -1466,7 +1335,7 @@ size_t pderead_residual_workspace_bytes(const pderead_net* sol, const pderead_ne
     size_t bytes = 0;
     bytes += align_up(packed_floats(U) * 4, 256) * (need_backward ? 2 : 1);
     bytes += align_up(packed_floats(N) * 4, 256) * (need_backward ? 2 : 1);
-    bytes += (align_up(tc_image_bytes_bound(U), 256) + align_up(tc_image_bytes_bound(N), 256)) * (need_backward ? 2 : 1);
+    bytes += align_up(tc_image_bytes_bound(U), 256) + align_up(tc_image_bytes_bound(N), 256);
     bytes += align_up((size_t)chunk * (n + 1) * 4, 256) + align_up((size_t)chunk * 4, 256);   // dxn, dtm
     if (need_backward) {
         const GradLayout lu = make_layout(U), ln = make_layout(N);

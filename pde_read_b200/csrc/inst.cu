@@ -16,6 +16,5 @@ template int launch_tc_fwd<PDR_ACT, PDR_NX, PDR_NT>(const TcFwdArgs&, cudaStream
 #if PDR_BWD
 template int bwd_grid<PDR_ACT, PDR_NX, PDR_NT>(int, int, int, long long, int*);
 template int launch_bwd_impl<PDR_ACT, PDR_NX, PDR_NT>(const BwdArgs&, int, cudaStream_t);
-template int launch_tc_bwd<PDR_ACT, PDR_NX, PDR_NT>(const TcBwdArgs&, int, cudaStream_t);
 #endif
 }  // namespace pdr

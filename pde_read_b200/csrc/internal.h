@@ -126,52 +126,12 @@ struct TcFwdArgs {
     long long num_tiles;
     float* out0;
     float* out1;
-    float* stash;             // [L-1][M][J][mrows] pre-activations of hidden layers 1..L-1 (null unless STASH)
     const float* dtm_in;
     float* resid_out;
     float* seed_out;
     const float* grad_resid;
     float seed_scale;
     double* sumsq;
-};
-
-// geometry of the tensor-core reverse kernel (tc_jet_bwd_kernel)
-struct TcBwdGeom {
-    int mrows, Kpad, NB;
-    int Jp;           // columns per point (J rounded up so that operand stores stay 16-byte aligned)
-    int PC;           // points per chunk (per sub)
-    int nchunk;       // chunks per tile (2 = ping-pong, 1 when shared memory is short)
-    int NC;           // PC * Jp  (K of the weight-gradient products, multiple of 8)
-    int NCpad;        // N of the hbar products (NC rounded up to the MMA granularity)
-    int TP;           // points per tile
-    int a_bytes, a_rs;        // W^T image half
-    int zt_bytes, zt_rs;      // zbar as B operand of hbar = W^T zbar:   [n][k]  (k-contiguous, 144-byte k-group stride)
-    int za_bytes, za_rs;      // zbar as A operand of gW = zbar y^T:     [row][n] (n-contiguous)
-    int yb_bytes;             // y of the layer below as B operand of gW: [k][n]  (same row stride za_rs)
-    int npad_w;               // N of the weight-gradient products (Kpad rounded up to the MMA granularity)
-    int set_bytes;            // one (sub, chunk) set: hi|lo of zt, za, yb
-    int sub_stride;
-    int nwbuf;
-    int gcol0;                // first TMEM column of the weight-gradient accumulators
-    int tmem_cols;
-    size_t smem_bytes;
-};
-
-struct TcBwdArgs {
-    NetDev net;
-    GradLayout lay;
-    TcBwdGeom geom;
-    const float* wimg;        // transposed weight images: index lv-1 for hidden layer lv = 1..L-1, index L-1 = input layer (for gin)
-    const float* in;          // [M][din]
-    long long M;
-    long long num_tiles;
-    const float* stash;       // [L-1][M][J][mrows]
-    const float* g0;
-    const float* g1;
-    float g0_scale, g1_scale;
-    float* gin;               // [M][din] or null (J == 1 only)
-    float* gpart;             // [gridDim.x][lay.total]
-    int accumulate;
 };
 
 struct Segment {
@@ -201,8 +161,6 @@ int launch_plain_bwd(const BwdArgs& a, int grid, cudaStream_t stream);
 
 template <int ACT, int NX, int NT>
 int launch_tc_fwd(const TcFwdArgs& a, cudaStream_t stream);
-template <int ACT, int NX, int NT>
-int launch_tc_bwd(const TcBwdArgs& a, int grid, cudaStream_t stream);
 
 // geometry helpers shared by host code
 inline int jet_len(int nx, int nt) { return 1 + nx + nt; }

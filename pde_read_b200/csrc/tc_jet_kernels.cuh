@@ -1,4 +1,7 @@
-// Tensor-core (tcgen05 / TMEM) MLP-jet kernels for sm_100a.
+// Tensor-core (tcgen05 / TMEM) MLP-jet FORWARD kernel for sm_100a (forward-only calls: Evaluate_Derivatives,
+// PDE_Residual without grad, Discovery_Testing, extraction).  Round 1 also carried a reverse kernel on this path; it
+// lost to the CUDA-core reverse kernel on every shape (3xTF32 needs zbar in two operand layouts and y in one, each as
+// hi | lo: 6 fp32 copies of a tile in shared memory leave room for 16-point chunks only) and was removed in round 2.
 //
 // Same math as mlp_jet_kernels.cuh (reference Network.py:174-202 + the nested autograd of
 // PDE_Residual.py:92-145, replaced by Taylor-jet propagation), but the hidden-layer products
@@ -29,7 +32,6 @@ namespace pdr {
 
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;   // + MMA warp + weight-loader warp
-constexpr int TC_FLUSH_TILES = 2;   // the TMEM weight-gradient accumulators are drained every this many tiles
 constexpr uint32_t TC_B_CS = 144;                      // byte stride between 4-k groups of the B operand (bank spread)
 
 // ---- small PTX helpers not in umma.cuh -------------------------------------------------------
@@ -68,7 +70,7 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
 }
 
 // ---- forward ------------------------------------------------------------------------------------
-template <int ACT, int NX, int NT, int MROWS, bool STASH>
+template <int ACT, int NX, int NT, int MROWS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_jet_fwd_kernel(const TcFwdArgs a) {
     constexpr int J = 1 + NX + NT;
     constexpr int SUBS = (MROWS == 64) ? 2 : 1;
@@ -259,12 +261,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_jet_fwd_kernel(const TcFwdAr
                             for (int j = 0; j < J; ++j) z[j] = __uint_as_float(raw[gq * J + j]) + __uint_as_float(rawc[gq * J + j]);
                             if (!is_out) {
                                 z[0] += bias;
-                                if (STASH && p0 + pt < a.M) {
-                                    // [layer][point][jet][row]: consecutive lanes -> consecutive addresses
-                                    float* sp = a.stash + ((size_t)(gi - 1) * a.M + (size_t)(p0 + pt)) * (size_t)(J * MROWS) + row;
-#pragma unroll
-                                    for (int j = 0; j < J; ++j) sp[j * MROWS] = z[j];
-                                }
                                 if (active) {
                                     float y[J];
                                     act_fwd<ACT, NX, NT, float>(z, ab, y);
@@ -331,456 +327,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_jet_fwd_kernel(const TcFwdAr
 }
 
 
-// ---- backward -------------------------------------------------------------------------------------
-// Reverse pass of tc_jet_fwd_kernel for one network.  Per hidden layer lv (top first) the epilogue
-// warps turn ybar^lv (from the output seeds, or from TMEM) into zbar^lv with the hand-written
-// activation VJP and re-evaluate y^(lv-1) from the stashed pre-activations; both go to shared memory
-// as tensor-core operands and the MMA thread issues
-//     hbar^(lv-1)[k][n] = sum_i W_lv[i][k] zbar^lv[i][n]          (A = W_lv^T image, B = zbar [n][i])
-//     gW_lv[i][k]      += sum_n zbar^lv[i][n] y^(lv-1)[k][n]      (A = zbar [i][n],   B = y [k][n])
-// The weight-gradient accumulators stay in TMEM for the whole kernel and are flushed once at the end;
-// bias / input-layer / output-layer / rational-coefficient gradients are thread-local sums (thread =
-// neuron) collected in shared memory.
-template <int J>
-struct TcCols {
-    static constexpr int Jp = (J == 3) ? 4 : (J == 5) ? 6 : (J == 7) ? 8 : J;   // columns per point
-    static constexpr int GB = (Jp == 1) ? 8 : (Jp == 2) ? 4 : 2;                 // points per group (backward)
-};
-
-template <int ACT, int NX, int NT, int MROWS>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_jet_bwd_kernel(const TcBwdArgs a) {
-    constexpr int J = 1 + NX + NT;
-    constexpr int Jp = TcCols<J>::Jp;
-    constexpr int G = TcCols<J>::GB;
-    constexpr int GC = G * Jp;                 // columns per group (multiple of 4)
-    constexpr int SUBS = (MROWS == 64) ? 2 : 1;
-    using namespace umma;
-
-    extern __shared__ __align__(128) unsigned char tc_smem_b[];
-    unsigned char* smem = tc_smem_b;
-    const NetDev& net = a.net;
-    const TcBwdGeom& g = a.geom;
-    const int W = net.W, L = net.L, din = net.din;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int TP = g.TP, PC = g.PC, NCH = g.nchunk;
-    const bool want_gin = (a.gin != nullptr);
-
-    const int sbL = L * W, sw0 = sbL + 1, swout = sw0 + W * din, sab = swout + W, NS = sab + 7 * L;
-    unsigned char* wbuf = smem;
-    unsigned char* slots = wbuf + (size_t)g.nwbuf * 2 * g.a_bytes;
-    float* IN = reinterpret_cast<float*>(slots + (size_t)SUBS * g.sub_stride);   // [din][TP]
-    float* SD = IN + din * TP;                                                    // [J][TP]
-    float* SACC = SD + J * TP;                                                    // [NS]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(SACC + ((NS + 1) & ~1));
-    uint64_t* full = bars;
-    uint64_t* dready = bars + 2;
-    uint64_t* wfull = bars + 4;
-    uint64_t* wfree = bars + 6;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-
-    float* gp = a.gpart + (size_t)blockIdx.x * a.lay.total;
-    {
-        uint4* p = reinterpret_cast<uint4*>(slots);
-        const int n16 = (SUBS * g.sub_stride) >> 4;
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
-        for (int i = threadIdx.x; i < NS; i += blockDim.x) SACC[i] = 0.f;
-        if (!a.accumulate)
-            for (int i = threadIdx.x; i < a.lay.total; i += blockDim.x) gp[i] = 0.f;
-    }
-    if (threadIdx.x == 0) {
-        for (int c = 0; c < 2; ++c) {
-            mbar_init(&full[c], TC_EPI_WARPS);
-            mbar_init(&dready[c], 1);
-            mbar_init(&wfull[c], 1);
-            mbar_init(&wfree[c], 1);
-        }
-        fence_mbar_init();
-    }
-    if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, (uint32_t)g.tmem_cols);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const long long my_tiles = (a.num_tiles > blockIdx.x) ? (a.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int nprod = (L - 1) + (want_gin ? 1 : 0);
-    const long long total_prod = my_tiles * nprod;
-    const uint32_t img_bytes = 2u * (uint32_t)g.a_bytes;
-    const uint32_t half_set = (uint32_t)(g.zt_bytes + g.za_bytes + g.yb_bytes);   // hi part of a set; lo follows
-
-    if (warp == TC_EPI_WARPS + 1) {
-        // ===== weight loader =====
-        if (lane == 0) {
-            const long long nload = (nprod <= g.nwbuf) ? (total_prod < nprod ? total_prod : nprod) : total_prod;
-            for (long long s = 0; s < nload; ++s) {
-                const int b = (int)(s % g.nwbuf);
-                if (s >= g.nwbuf) mbar_wait(&wfree[b], (uint32_t)(((s / g.nwbuf) - 1) & 1));
-                const int idx = (int)(s % nprod);
-                const int img = (idx < L - 1) ? (L - 2 - idx) : (L - 1);
-                mbar_expect_tx(&wfull[b], img_bytes);
-                bulk_g2s(wbuf + (size_t)b * img_bytes, reinterpret_cast<const unsigned char*>(a.wimg) + (size_t)img * img_bytes,
-                         img_bytes, &wfull[b]);
-            }
-        }
-    } else if (warp == TC_EPI_WARPS) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc_d = make_idesc_tf32(MROWS, g.NCpad, 0, 0);
-            const uint32_t idesc_w = make_idesc_tf32(MROWS, g.npad_w, 0, 0);
-            const int ks_d = g.Kpad >> 3, ks_w = g.NC >> 3;
-            const uint32_t corr_off = (uint32_t)(NCH * g.NCpad);   // correction-term accumulators of the hbar products
-            uint32_t full_ph[2] = {0, 0};
-            for (long long s = 0; s < total_prod; ++s) {
-                const int idx = (int)(s % nprod);
-                const int b = (nprod <= g.nwbuf) ? idx : (int)(s % g.nwbuf);
-                const bool first_tile = ((s / nprod) % TC_FLUSH_TILES) == 0;   // accumulators were flushed: restart them
-                const bool resident = (nprod <= g.nwbuf);
-                if (!resident || s < nprod) mbar_wait(&wfull[b], (uint32_t)((s / g.nwbuf) & 1));
-                const uint32_t a_hi = smem_u32(wbuf + (size_t)b * img_bytes), a_lo = a_hi + (uint32_t)g.a_bytes;
-                for (int c = 0; c < NCH; ++c) {
-                    mbar_wait(&full[c], full_ph[c]);
-                    full_ph[c] ^= 1;
-                    tc_fence_after();
-#pragma unroll
-                    for (int sub = 0; sub < SUBS; ++sub) {
-                        const uint32_t set_hi = smem_u32(slots + (size_t)sub * g.sub_stride + (size_t)c * g.set_bytes);
-                        const uint32_t set_lo = set_hi + half_set;
-                        const uint32_t lane_off = (uint32_t)(sub * 16) << 16;
-                        // hbar (or the input gradient): D[k][n] = sum_i A[k][i] * zbar[n][i]
-                        {
-                            const uint32_t d_addr = tmem_base + lane_off + (uint32_t)(c * g.NCpad);
-                            for (int ks = 0; ks < ks_d; ++ks) {
-                                const uint64_t dah = make_smem_desc(a_hi + ks * 256u, 128u, (uint32_t)g.a_rs);
-                                const uint64_t dal = make_smem_desc(a_lo + ks * 256u, 128u, (uint32_t)g.a_rs);
-                                const uint64_t dbh = make_smem_desc(set_hi + ks * 2u * TC_B_CS, TC_B_CS, (uint32_t)g.zt_rs);
-                                const uint64_t dbl = make_smem_desc(set_lo + ks * 2u * TC_B_CS, TC_B_CS, (uint32_t)g.zt_rs);
-                                mma_tf32_ss(d_addr, dah, dbh, idesc_d, ks > 0);
-                                mma_tf32_ss(d_addr + corr_off, dal, dbh, idesc_d, ks > 0);
-                                mma_tf32_ss(d_addr + corr_off, dah, dbl, idesc_d, 1);
-                            }
-                        }
-                        if (idx < L - 1) {
-                            // gW_lv[i][k] += sum_n zbar[i][n] * y[k][n]
-                            const int lv = L - 1 - idx;
-                            const uint32_t d_addr = tmem_base + lane_off + (uint32_t)(g.gcol0 + (lv - 1) * g.npad_w);
-                            const uint32_t za_hi = set_hi + (uint32_t)g.zt_bytes, za_lo = set_lo + (uint32_t)g.zt_bytes;
-                            const uint32_t yb_hi = za_hi + (uint32_t)g.za_bytes, yb_lo = za_lo + (uint32_t)g.za_bytes;
-                            for (int ks = 0; ks < ks_w; ++ks) {
-                                const uint64_t dah = make_smem_desc(za_hi + ks * 256u, 128u, (uint32_t)g.za_rs);
-                                const uint64_t dal = make_smem_desc(za_lo + ks * 256u, 128u, (uint32_t)g.za_rs);
-                                const uint64_t dbh = make_smem_desc(yb_hi + ks * 256u, 128u, (uint32_t)g.za_rs);
-                                const uint64_t dbl = make_smem_desc(yb_lo + ks * 256u, 128u, (uint32_t)g.za_rs);
-                                mma_tf32_ss(d_addr, dah, dbh, idesc_w, !(first_tile && c == 0 && ks == 0));
-                                mma_tf32_ss(d_addr, dal, dbh, idesc_w, 1);
-                                mma_tf32_ss(d_addr, dah, dbl, idesc_w, 1);
-                            }
-                        }
-                    }
-                    mma_commit(&dready[c]);
-                }
-                if (!resident) mma_commit(&wfree[b]);
-            }
-        }
-    } else {
-        // ===== epilogue warps =====
-        const int qd = warp & 3, half = warp >> 2;
-        const int sub = (MROWS == 64) ? (lane >> 4) : 0;
-        const int rl = (MROWS == 64) ? (lane & 15) : lane;
-        const int row = (MROWS == 64) ? (16 * qd + rl) : (32 * qd + rl);
-        const int nid = qd * g.NB + rl;
-        const bool active = (rl < g.NB) && (nid < W);
-        const uint32_t lane_taddr = tmem_base + ((uint32_t)(32 * qd) << 16);
-        const uint32_t koff = (uint32_t)(nid & 3) * 4u + (uint32_t)(nid >> 2) * TC_B_CS;
-        const uint32_t za_row = (uint32_t)(row & 7) * 16u + (uint32_t)(row >> 3) * (uint32_t)g.za_rs;
-        const uint32_t yb_row = (uint32_t)(nid & 7) * 16u + (uint32_t)(nid >> 3) * (uint32_t)g.za_rs;
-        const int PH = PC >> 1;
-        const int et = threadIdx.x;
-        uint32_t dr_ph[2] = {0, 0};
-        const float* wout = net.w[L];
-        const size_t srow = (size_t)(J * MROWS);
-        long long tiles_done = 0;
-
-        for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-            const long long p0 = tile * TP;
-            for (int idx = et; idx < din * TP; idx += TC_EPI_WARPS * 32) {
-                const int pt = idx / din, d = idx - pt * din;
-                const long long p = p0 + pt;
-                IN[d * TP + pt] = (p < a.M) ? __ldg(a.in + p * din + d) : 0.f;
-            }
-            for (int idx = et; idx < J * TP; idx += TC_EPI_WARPS * 32) {
-                const int j = idx / TP, pt = idx - j * TP;
-                const long long p = p0 + pt;
-                float sd = 0.f;
-                if (p < a.M) {
-                    if (J == 1) {
-                        sd = a.g0 ? a.g0_scale * __ldg(a.g0 + p) : 0.f;
-                    } else if (j <= NX) {
-                        float f = 1.f;
-#pragma unroll
-                        for (int t = 2; t <= NX; ++t) if (t <= j) f *= (float)t;
-                        sd = a.g0 ? a.g0_scale * f * __ldg(a.g0 + p * (NX + 1) + j) : 0.f;
-                    } else if (j == NX + NT) {
-                        float f = 1.f;
-#pragma unroll
-                        for (int t = 2; t <= NT; ++t) f *= (float)t;
-                        sd = a.g1 ? a.g1_scale * f * __ldg(a.g1 + p) : 0.f;
-                    }
-                }
-                SD[idx] = sd;
-            }
-            epi_bar_sync();
-            if (warp == 0) {   // output bias: sum of the order-0 seeds
-                float sb = 0.f;
-                for (int pt = lane; pt < TP; pt += 32) sb += SD[pt];
-                sb = warp_sum(sb);
-                if (lane == 0) SACC[sbL] += sb;
-            }
-
-            for (int lv = L - 1; lv >= 0; --lv) {
-                const bool top = (lv == L - 1);
-                const bool feeds_mma = (lv >= 1) || want_gin;
-                float ab[7], ab_lo[7], abbar[7];
-                load_ab<ACT>(net, lv, ab);
-                load_ab<ACT>(net, lv >= 1 ? lv - 1 : 0, ab_lo);
-#pragma unroll
-                for (int t = 0; t < 7; ++t) abbar[t] = 0.f;
-                const float wo = (top && active) ? __ldg(wout + nid) : 0.f;
-                const float* st_z = (lv >= 1) ? a.stash + ((size_t)(lv - 1) * a.M + (size_t)p0) * srow + row : nullptr;
-                const float* st_zp = (lv >= 2) ? a.stash + ((size_t)(lv - 2) * a.M + (size_t)p0) * srow + row : nullptr;
-
-                for (int c = 0; c < NCH; ++c) {
-                    // stash reads do not depend on the tensor core: issue the first group's before waiting for it
-                    float zn[G][J], zpn[G][J];
-                    auto fetch = [&](int q0f) {
-#pragma unroll
-                        for (int gq = 0; gq < G; ++gq) {
-                            const int pt = (sub * NCH + c) * PC + half * PH + q0f + gq;
-                            const bool valid = active && (p0 + pt) < a.M;
-#pragma unroll
-                            for (int j = 0; j < J; ++j) {
-                                zn[gq][j] = (lv >= 1 && valid) ? __ldcs(st_z + (size_t)pt * srow + j * MROWS) : 0.f;
-                                zpn[gq][j] = (lv >= 2 && valid) ? __ldcs(st_zp + (size_t)pt * srow + j * MROWS) : 0.f;
-                            }
-                        }
-                    };
-                    fetch(0);
-                    if (!top) {
-                        mbar_wait(&dready[c], dr_ph[c]);
-                        dr_ph[c] ^= 1;
-                        tc_fence_after();
-                    }
-                    unsigned char* set_hi = slots + (size_t)sub * g.sub_stride + (size_t)c * g.set_bytes;
-                    unsigned char* set_lo = set_hi + half_set;
-                    float gb = 0.f, gwo = 0.f, gx = 0.f, gt = 0.f;
-                    float gwin[MAXD];
-#pragma unroll
-                    for (int d = 0; d < MAXD; ++d) gwin[d] = 0.f;
-
-                    for (int q0 = 0; q0 < PH; q0 += G) {
-                        const int pp0 = half * PH + q0;
-                        float zc[G][J], zpc[G][J];
-#pragma unroll
-                        for (int gq = 0; gq < G; ++gq)
-#pragma unroll
-                            for (int j = 0; j < J; ++j) { zc[gq][j] = zn[gq][j]; zpc[gq][j] = zpn[gq][j]; }
-                        if (q0 + G < PH) fetch(q0 + G);
-                        uint32_t raw[GC], rawc[GC];
-                        if (!top) {
-                            tmem_ld_cols<GC>(lane_taddr + (uint32_t)(c * g.NCpad + pp0 * Jp), raw);
-                            tmem_ld_cols<GC>(lane_taddr + (uint32_t)((NCH + c) * g.NCpad + pp0 * Jp), rawc);
-                            tmem_wait_ld();
-                        }
-                        float zb[GC], yp[GC];
-#pragma unroll
-                        for (int t = 0; t < GC; ++t) { zb[t] = 0.f; yp[t] = 0.f; }
-                        if (active) {
-#pragma unroll
-                            for (int gq = 0; gq < G; ++gq) {
-                                const int pt = (sub * NCH + c) * PC + pp0 + gq;
-                                float z[J], ybar[J], zbar[J];
-                                if (lv == 0) {
-                                    input_layer_jet<NX, NT>(net, IN, TP, nid, pt, z);
-                                } else {
-#pragma unroll
-                                    for (int j = 0; j < J; ++j) z[j] = zc[gq][j];
-                                }
-                                if (top) {
-                                    float y[J];
-                                    act_fwd<ACT, NX, NT, float>(z, ab, y);
-#pragma unroll
-                                    for (int j = 0; j < J; ++j) {
-                                        const float sd = SD[j * TP + pt];
-                                        ybar[j] = wo * sd;
-                                        gwo = fmaf(sd, y[j], gwo);
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int j = 0; j < J; ++j)
-                                        ybar[j] = __uint_as_float(raw[gq * Jp + j]) + __uint_as_float(rawc[gq * Jp + j]);
-                                }
-                                act_vjp<ACT, NX, NT, float>(z, ab, ybar, zbar, abbar);
-                                gb += zbar[0];
-#pragma unroll
-                                for (int j = 0; j < J; ++j) zb[gq * Jp + j] = zbar[j];
-                                if (lv == 0) {
-                                    if (NX > 0) gx += zbar[1];
-                                    if (NT > 0) gt += zbar[NX + 1];
-#pragma unroll
-                                    for (int d = 0; d < MAXD; ++d)
-                                        if (d < din) gwin[d] = fmaf(zbar[0], IN[d * TP + pt], gwin[d]);
-                                } else {
-                                    float zp[J], y1[J];
-                                    if (lv == 1) {
-                                        input_layer_jet<NX, NT>(net, IN, TP, nid, pt, zp);
-                                    } else {
-#pragma unroll
-                                        for (int j = 0; j < J; ++j) zp[j] = zpc[gq][j];
-                                    }
-                                    act_fwd<ACT, NX, NT, float>(zp, ab_lo, y1);
-#pragma unroll
-                                    for (int j = 0; j < J; ++j) yp[gq * Jp + j] = y1[j];
-                                }
-                            }
-                            if (feeds_mma) {
-                                // operand stores: zbar as [n][k] (scalar) and, for the weight gradient, zbar [row][n] and
-                                // y [k][n] (16-byte vectors: the group's GC columns are contiguous and 4-aligned)
-                                const int n0 = pp0 * Jp;
-                                float zh[GC], zl[GC];
-#pragma unroll
-                                for (int t = 0; t < GC; ++t) tf32_split(zb[t], zh[t], zl[t]);
-#pragma unroll
-                                for (int t = 0; t < GC; ++t) {
-                                    if ((t % Jp) < J) {
-                                        const int n = n0 + t;
-                                        const uint32_t off = (uint32_t)(n & 7) * 16u + (uint32_t)(n >> 3) * (uint32_t)g.zt_rs + koff;
-                                        *reinterpret_cast<float*>(set_hi + off) = zh[t];
-                                        *reinterpret_cast<float*>(set_lo + off) = zl[t];
-                                    }
-                                }
-                                if (lv >= 1) {
-                                    unsigned char* za_h = set_hi + g.zt_bytes + za_row + (uint32_t)(n0 >> 2) * 128u;
-                                    unsigned char* za_l = set_lo + g.zt_bytes + za_row + (uint32_t)(n0 >> 2) * 128u;
-                                    unsigned char* yb_h = set_hi + g.zt_bytes + g.za_bytes + yb_row + (uint32_t)(n0 >> 2) * 128u;
-                                    unsigned char* yb_l = set_lo + g.zt_bytes + g.za_bytes + yb_row + (uint32_t)(n0 >> 2) * 128u;
-#pragma unroll
-                                    for (int t4 = 0; t4 < GC / 4; ++t4) {
-                                        *reinterpret_cast<float4*>(za_h + t4 * 128) = make_float4(zh[4 * t4], zh[4 * t4 + 1], zh[4 * t4 + 2], zh[4 * t4 + 3]);
-                                        *reinterpret_cast<float4*>(za_l + t4 * 128) = make_float4(zl[4 * t4], zl[4 * t4 + 1], zl[4 * t4 + 2], zl[4 * t4 + 3]);
-                                        float yh[4], yl[4];
-#pragma unroll
-                                        for (int u = 0; u < 4; ++u) tf32_split(yp[4 * t4 + u], yh[u], yl[u]);
-                                        *reinterpret_cast<float4*>(yb_h + t4 * 128) = make_float4(yh[0], yh[1], yh[2], yh[3]);
-                                        *reinterpret_cast<float4*>(yb_l + t4 * 128) = make_float4(yl[0], yl[1], yl[2], yl[3]);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    if (active) {
-                        atomicAdd(&SACC[lv * W + nid], gb);
-                        if (top) atomicAdd(&SACC[swout + nid], gwo);
-                        if (lv == 0) {
-                            if (NX > 0) gwin[1] += gx;
-                            if (NT > 0) gwin[0] += gt;
-#pragma unroll
-                            for (int d = 0; d < MAXD; ++d)
-                                if (d < din) atomicAdd(&SACC[sw0 + nid * din + d], gwin[d]);
-                        }
-                    }
-                    if (feeds_mma) {
-                        fence_proxy_async();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&full[c]);
-                    } else {
-                        tc_fence_before();
-                    }
-                }
-                if (ACT == ACT_RATIONAL) {
-#pragma unroll
-                    for (int t = 0; t < 7; ++t) {
-                        const float sv = warp_sum(abbar[t]);
-                        if (lane == 0) atomicAdd(&SACC[sab + 7 * lv + t], sv);
-                    }
-                }
-            }
-
-            if (want_gin) {
-                // input gradient (plain networks only): rows d < din of the last product
-                for (int c = 0; c < NCH; ++c) {
-                    mbar_wait(&dready[c], dr_ph[c]);
-                    dr_ph[c] ^= 1;
-                    tc_fence_after();
-                    if (qd == 0) {
-                        for (int q = 0; q < PH; ++q) {
-                            const int pp = half * PH + q;
-                            uint32_t r1[1], r2[1];
-                            tmem_ld_cols<1>(lane_taddr + (uint32_t)(c * g.NCpad + pp * Jp), r1);
-                            tmem_ld_cols<1>(lane_taddr + (uint32_t)((NCH + c) * g.NCpad + pp * Jp), r2);
-                            tmem_wait_ld();
-                            const int pt = (sub * NCH + c) * PC + pp;
-                            const long long p = p0 + pt;
-                            if (rl < din && p < a.M) a.gin[p * din + rl] = __uint_as_float(r1[0]) + __uint_as_float(r2[0]);
-                        }
-                    }
-                    tc_fence_before();
-                }
-            }
-
-            // ---- drain the TMEM weight-gradient accumulators every TC_FLUSH_TILES tiles (and after the last
-            //      tile): long fp32 accumulation chains inside the tensor core drift, these adds round to nearest.
-            //      All products of this tile have completed (every warp waited for their commits above). ----
-            ++tiles_done;
-            if ((tiles_done % TC_FLUSH_TILES) == 0 || tile + gridDim.x >= a.num_tiles) {
-                tc_fence_after();
-                if (half == 0) {
-                    for (int l = 1; l < L; ++l) {
-                        const uint32_t gcol = (uint32_t)(g.gcol0 + (l - 1) * g.npad_w);
-                        for (int k0 = 0; k0 < g.Kpad; k0 += 8) {
-                            uint32_t v[8];
-                            tmem_ld_x8(lane_taddr + gcol + (uint32_t)k0, v);
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int t = 0; t < 8; ++t) {
-                                float f = __uint_as_float(v[t]);
-                                if (MROWS == 64) f += __shfl_xor_sync(0xffffffffu, f, 16);
-                                const int k = k0 + t;
-                                if (active && sub == 0 && k < W) atomicAdd(&gp[a.lay.off_w[l] + nid * W + k], f);   // RED: no round trip
-                            }
-                        }
-                    }
-                }
-                tc_fence_before();
-            }
-        }
-
-        // ---- flush the small-parameter sums (shared memory) ----
-        epi_bar_sync();
-        for (int idx = et; idx < NS; idx += TC_EPI_WARPS * 32) {
-            int dst;
-            if (idx < sbL) {
-                const int l = idx / W;
-                dst = a.lay.off_b[l] + (idx - l * W);
-            } else if (idx == sbL) {
-                dst = a.lay.off_b[L];
-            } else if (idx < swout) {
-                dst = a.lay.off_w[0] + (idx - sw0);
-            } else if (idx < sab) {
-                dst = a.lay.off_w[L] + (idx - swout);
-            } else {
-                const int l = (idx - sab) / 7;
-                dst = a.lay.off_ab[l] + (idx - sab - 7 * l);
-            }
-            gp[dst] += SACC[idx];
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == TC_EPI_WARPS) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
-}
-
 // ---- launcher -----------------------------------------------------------------------------------
 template <int ACT, int NX, int NT>
 int launch_tc_fwd(const TcFwdArgs& a, cudaStream_t stream) {
@@ -791,34 +337,14 @@ int launch_tc_fwd(const TcFwdArgs& a, cudaStream_t stream) {
     if (grid > a.num_tiles) grid = a.num_tiles;
     if (grid < 1) grid = 1;
     const size_t smem = a.geom.smem_bytes;
-#define PDR_TC_LAUNCH(MR, ST)                                                                                            \
+#define PDR_TC_LAUNCH(MR)                                                                                                \
     do {                                                                                                                 \
-        const int rc_ = ensure_dynamic_smem((const void*)tc_jet_fwd_kernel<ACT, NX, NT, MR, ST>, smem);                  \
+        const int rc_ = ensure_dynamic_smem((const void*)tc_jet_fwd_kernel<ACT, NX, NT, MR>, smem);                      \
         if (rc_ != PDEREAD_OK) return rc_;                                                                               \
-        tc_jet_fwd_kernel<ACT, NX, NT, MR, ST><<<(int)grid, TC_THREADS, smem, stream>>>(a);                              \
+        tc_jet_fwd_kernel<ACT, NX, NT, MR><<<(int)grid, TC_THREADS, smem, stream>>>(a);                                  \
     } while (0)
-    if (a.geom.mrows == 64) {
-        if (a.stash) PDR_TC_LAUNCH(64, true); else PDR_TC_LAUNCH(64, false);
-    } else {
-        if (a.stash) PDR_TC_LAUNCH(128, true); else PDR_TC_LAUNCH(128, false);
-    }
+    if (a.geom.mrows == 64) PDR_TC_LAUNCH(64); else PDR_TC_LAUNCH(128);
 #undef PDR_TC_LAUNCH
-    PDR_CUDA_CHECK(cudaGetLastError());
-    return PDEREAD_OK;
-}
-
-template <int ACT, int NX, int NT>
-int launch_tc_bwd(const TcBwdArgs& a, int grid, cudaStream_t stream) {
-    const size_t smem = a.geom.smem_bytes;
-    if (a.geom.mrows == 64) {
-        const int rc = ensure_dynamic_smem((const void*)tc_jet_bwd_kernel<ACT, NX, NT, 64>, smem);
-        if (rc != PDEREAD_OK) return rc;
-        tc_jet_bwd_kernel<ACT, NX, NT, 64><<<grid, TC_THREADS, smem, stream>>>(a);
-    } else {
-        const int rc = ensure_dynamic_smem((const void*)tc_jet_bwd_kernel<ACT, NX, NT, 128>, smem);
-        if (rc != PDEREAD_OK) return rc;
-        tc_jet_bwd_kernel<ACT, NX, NT, 128><<<grid, TC_THREADS, smem, stream>>>(a);
-    }
     PDR_CUDA_CHECK(cudaGetLastError());
     return PDEREAD_OK;
 }

@@ -1,15 +1,12 @@
-"""GPU parity tests of the tensor-core kernels (tcgen05 / TMEM, 3xTF32), forced on with
+"""GPU parity tests of the tensor-core forward kernel (tcgen05 / TMEM, 3xTF32), forced on with
 pderead_debug_set_tensor_cores(2), against the golden vectors of the unmodified reference, the CPU
 oracle, and the CUDA-core kernels.
 
-Stated tolerances for this path (metric max|ours-ref|/max|ref| per output column):
-  * derivatives: the same per-order tolerances as the CUDA-core path (order 0-2: 1e-5, 3: 2e-5, 4: 5e-5);
-  * residual: 1e-4;
-  * parameter gradients of randomly initialised networks: 1e-4;
-  * parameter gradients at the TRAINED checkpoint: 1e-3.  There |R| is ~1e-2 of |D_t U| and |N|, so the
-    3xTF32 forward error (~1e-6 relative, caused by the tensor core truncating inside its accumulation)
-    becomes ~1e-4 relative in the seeds 2R/M.  This is why mode "auto" keeps the gradient path on the
-    CUDA cores (fp32 accumulation, gradients within 1e-4 here); see DESIGN.md section 8.
+Stated tolerances for this path (metric max|ours-ref|/max|ref| per output column): derivatives: the same
+per-order tolerances as the CUDA-core path (order 0-2: 1e-5, 3: 2e-5, 4: 5e-5); residual: 1e-4.
+The gradient path never uses the tensor cores: at a TRAINED network |R| is ~1e-2 of |D_t U| and |N|, so the
+3xTF32 forward error (~1e-6 relative, the tensor core truncates inside its accumulation) becomes ~1e-4 relative
+in the seeds 2R/M (round 1 measured 3.6e-4 on the gradients of the shipped checkpoint); see DESIGN.md.
 """
 import numpy as np
 import pytest
@@ -41,8 +38,9 @@ def _launch_names(fn):
 
 
 def test_policy_selects_the_expected_kernels():
-    """auto: forward-only calls of width > 64 run tc_jet_fwd_kernel; width <= 64 and the whole gradient
-    path run the CUDA-core kernels; force: tc kernels on both; off: never."""
+    """auto: forward-only jet calls of width > 64 run tc_jet_fwd_kernel; width <= 64, plain-MLP calls and the whole
+    gradient path run the CUDA-core kernels; force: the tensor-core forward for narrow forward-only calls too, the
+    gradient path still on the CUDA cores; off: never."""
     from pde_read_b200 import _lib, functional as F
     lib = _lib.load()
     prev = lib.pderead_debug_set_tensor_cores(1)
@@ -59,9 +57,13 @@ def test_policy_selects_the_expected_kernels():
         assert not any("tc_jet" in n for n in names) and any("mlp_jet_fwd_kernel" in n for n in names), names
         names = _launch_names(lambda: F.collocation_loss_grad(sw, tw, sp, tp, 1, 2, P))
         assert not any("tc_jet" in n for n in names) and any("mlp_jet_bwd_kernel" in n for n in names), names
+        names = _launch_names(lambda: F.mlp_forward(sp, tp, torch.rand(500, 3, device=DEV)))
+        assert not any("tc_jet" in n for n in names) and any("mlp_plain_fwd_kernel" in n for n in names), names
         lib.pderead_debug_set_tensor_cores(2)
+        names = _launch_names(lambda: F.sol_derivatives_forward(sn_, tn_, 1, 2, P))
+        assert any("tc_jet_fwd_kernel" in n for n in names), names
         names = _launch_names(lambda: F.collocation_loss_grad(sn_, tn_, sp, tp, 1, 2, P))
-        assert any("tc_jet_bwd_kernel" in n for n in names) and any("tc_jet_fwd_kernel" in n for n in names), names
+        assert not any("tc_jet" in n for n in names) and any("mlp_jet_bwd_kernel" in n for n in names), names
         lib.pderead_debug_set_tensor_cores(0)
         names = _launch_names(lambda: F.sol_derivatives_forward(sw, tw, 1, 2, P))
         assert not any("tc_jet" in n for n in names), names
@@ -89,32 +91,9 @@ def test_tc_derivatives_against_reference_goldens(tc_force, name):
     assert_close_to_reference(R.detach().cpu().numpy(), z["resid"], z["resid_f64"], TOL_RESIDUAL, "resid")
 
 
-@pytest.mark.parametrize("act,L,W,m,n,M", [("Tanh", 5, 50, 1, 2, 3001), ("Rational", 5, 50, 1, 3, 1500),
-                                            ("Sin", 3, 24, 2, 2, 777), ("Tanh", 4, 64, 1, 2, 1000),
-                                            ("Rational", 2, 40, 1, 1, 129), ("Tanh", 2, 100, 1, 2, 515),
-                                            ("Rational", 3, 100, 1, 4, 300), ("Tanh", 3, 128, 1, 1, 64)])
-def test_tc_collocation_loss_and_gradients_against_oracle(tc_force, act, L, W, m, n, M):
-    """Collocation_Loss + backward with the tensor-core forward (with stash) and reverse kernels against the
-    float64 oracle; ragged M exercises the tile tails.  Networks the reverse tensor-core kernel cannot hold
-    (e.g. width 100 with 6 jets) fall back to the CUDA-core kernels for that network inside the same call."""
-    from pde_read_b200.Loss_Functions import Collocation_Loss
-    su = orc.init_network(L, W, 2, act, seed=11 + W)
-    sn = orc.init_network(max(2, L - 1), W, n + 1, act, seed=12 + W)
-    U, N = make_net(su, act, 2), make_net(sn, act, n + 1)
-    P = torch.rand(M, 2, generator=torch.Generator().manual_seed(M)) * 2 - 1
-    loss = Collocation_Loss(U, N, m, n, P.to(DEV), torch.float32, DEV)
-    loss.backward()
-    want, gs, gp = orc.collocation_loss_and_grads(to64(su), act, to64(sn), act, m, n, P.double())
-    w32, gs32, gp32 = orc.collocation_loss_and_grads(su, act, sn, act, m, n, P)
-    assert abs(loss.item() - want) <= 1e-5 * abs(want)
-    for net, ref64, ref32, tag in ((U, gs, gs32, "U."), (N, gp, gp32, "N.")):
-        for k, g in grads_of(net).items():
-            assert_close_to_reference(g, ref32[k].numpy(), ref64[k].numpy(), 1e-4, tag + k)
-
-
-def test_tc_matches_cuda_core_path_multi_chunk(tc_force):
-    """Large enough for several tiles per CTA, the periodic drain of the TMEM weight-gradient accumulators
-    and (with the workspace cap) several chunks: both kernel families must agree."""
+def test_tc_forward_matches_cuda_core_forward_multi_chunk(tc_force):
+    """Large enough for several tiles per CTA and (with the workspace cap) several chunks: residuals and sum(R^2) of
+    the forward-only call agree between the two kernel families."""
     from pde_read_b200 import functional as F
     su = orc.init_network(4, 48, 2, "Tanh", seed=5)
     sn = orc.init_network(3, 48, 3, "Tanh", seed=6)
@@ -125,22 +104,19 @@ def test_tc_matches_cuda_core_path_multi_chunk(tc_force):
     old = F.WORKSPACE_CAP_POINTS
     try:
         F.WORKSPACE_CAP_POINTS = 16_384
-        ss1, _, vu1, vn1, R1 = F.collocation_loss_grad(spu, tu, spn, tn, 1, 2, P, want_resid=True)
-        vu1, vn1 = [v.clone() for v in vu1], [v.clone() for v in vn1]
+        R1, ss1 = F.residual_forward(spu, tu, spn, tn, 1, 2, P)
         tc_force.pderead_debug_set_tensor_cores(0)
-        ss0, _, vu0, vn0, R0 = F.collocation_loss_grad(spu, tu, spn, tn, 1, 2, P, want_resid=True)
+        R0, ss0 = F.residual_forward(spu, tu, spn, tn, 1, 2, P)
     finally:
         F.WORKSPACE_CAP_POINTS = old
         F.release_workspaces()
     assert rel_err(ss1.cpu().numpy(), ss0.cpu().numpy()) < 1e-5
     assert rel_err(R1.cpu().numpy(), R0.cpu().numpy()) < TOL_RESIDUAL
-    for a, b in zip(vu1 + vn1, list(vu0) + list(vn0)):
-        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
 
 
-def test_tc_checkpoint_gradients_stated_tolerance(tc_force):
-    """Shipped Burgers checkpoint (trained: |R| << |D_t U|): derivatives and residual inside the common
-    tolerances, gradients inside the looser tolerance stated in the module docstring."""
+def test_tc_checkpoint_derivatives_and_residual(tc_force):
+    """Shipped Burgers checkpoint (trained: |R| << |D_t U|): derivatives, residual and loss of the tensor-core forward
+    inside the common tolerances; the gradients (CUDA-core path whatever the mode) inside 1e-4."""
     from pde_read_b200.Loss_Functions import Collocation_Loss
     from pde_read_b200.PDE_Residual import Evaluate_Derivatives, PDE_Residual
     ck, z = load_golden("burgers_ckpt.npz"), load_golden("burgers_colloc.npz")
@@ -159,7 +135,7 @@ def test_tc_checkpoint_gradients_stated_tolerance(tc_force):
     loss.backward()
     for pref, net in (("gsol.", U), ("gpde.", N)):
         for k, g in grads_of(net).items():
-            assert rel_err(g, z[pref + k + ".f64"]) < 1e-3, pref + k
+            assert rel_err(g, z[pref + k + ".f64"]) < 1e-4, pref + k
 
 
 def test_tc_extraction_matches_oracle_ranking(tc_force):
