@@ -96,7 +96,8 @@ int bwd_block_warps(int W, int L, int din, int J) {
     return (bwd_smem_bytes(W, L, din, J) > 112 * 1024 && nw < BWD_WIDE_WARPS) ? BWD_WIDE_WARPS : nw;
 }
 size_t fwd_smem_bytes_tile(int W, int din, int J, int nwarps, int TP) {
-    const int HS = J * TP + 4;
+    const int JP = (use_pair_map(J) && J > 1) ? ((J + 1) & ~1) : J;    // ProdTile::JP_FWD
+    const int HS = JP * TP + 4;
     return sizeof(float) * ((size_t)2 * W * HS + (size_t)din * TP + (size_t)nwarps * J * TP);
 }
 size_t fwd_smem_bytes(int W, int din, int J, int nwarps) { return fwd_smem_bytes_tile(W, din, J, nwarps, tile_points(J)); }
@@ -110,10 +111,12 @@ size_t bwd_smem_bytes(int W, int L, int din, int J) {
 // small helper kernels
 // ---------------------------------------------------------------------------------------------
 
-// wt[l][k][c*TNP+n] = W_{l+1}[c*TN+n][k]   (transposed, for z = W h)
-// wn[l][i][c*TNP+n] = W_{l+1}[i][c*TN+n]   (native,     for hbar = W^T zbar)
-__global__ void pack_weights_kernel(NetDev net, float* wt, float* wn) {
+// pair tile:  wt[l][k][c*TNP_PAIR+b*THP+n] = W_{l+1}[c*TN+b*TH+n][k]   (transposed, for z = W h)
+//             wn[l][i][c*TNP_PAIR+b*THP+n] = W_{l+1}[i][c*TN+b*TH+n]   (native,     for hbar = W^T zbar)
+// lane tile:  wt[l][k][c*TNP_LANE+n] = W_{l+1}[c*TN+n][k],  wn[l][i][c*TNP_LANE+n] = W_{l+1}[i][c*TN+n]
+__global__ void pack_weights_kernel(NetDev net, int pair, float* wt, float* wn) {
     const int W = net.W, NC = net.NC;
+    const int TNP = pair ? TNP_PAIR : TNP_LANE;
     const size_t per_layer = (size_t)W * NC * TNP;
     const size_t total = per_layer * (net.L - 1);
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -122,9 +125,17 @@ __global__ void pack_weights_kernel(NetDev net, float* wt, float* wn) {
         const size_t rem = idx - (size_t)l * per_layer;
         const int row = (int)(rem / (NC * TNP));
         const int col = (int)(rem - (size_t)row * (NC * TNP));
-        const int c = col / TNP, n = col - c * TNP;
-        const int o = c * TN + n;
-        const bool ok = (n < TN) && (o < W);
+        const int c = col / TNP, pos = col - c * TNP;
+        int o;
+        bool ok;
+        if (pair) {
+            const int half = pos / THP, n = pos - half * THP;
+            o = c * TN + half * TH + n;
+            ok = (n < TH) && (o < W);
+        } else {
+            o = c * TN + pos;
+            ok = (pos < TN) && (o < W);
+        }
         const float* w = net.w[l + 1];
         if (wt) wt[idx] = ok ? w[(size_t)o * W + row] : 0.f;
         if (wn) wn[idx] = ok ? w[(size_t)row * W + o] : 0.f;
@@ -870,11 +881,11 @@ static size_t packed_floats_old(const NetDev& n) { return (size_t)(n.L > 1 ? n.L
 static size_t stash_floats_per_point(const NetDev& n, int J) { return (size_t)(n.L > 1 ? n.L - 1 : 0) * n.W * J; }
 static size_t stash_floats_bound(const NetDev& n, int J) { return stash_floats_per_point(n, J); }
 
-static int pack(const NetDev& n, float* wt, float* wn, cudaStream_t s) {
+static int pack(const NetDev& n, int J, float* wt, float* wn, cudaStream_t s) {
     if (n.L <= 1 || (!wt && !wn)) return PDEREAD_OK;
     const size_t total = packed_floats_old(n);
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    pack_weights_kernel<<<blocks, 256, 0, s>>>(n, wt, wn);
+    pack_weights_kernel<<<blocks, 256, 0, s>>>(n, use_pair_map(J) ? 1 : 0, wt, wn);
     PDR_CUDA_CHECK(cudaGetLastError());
     stage_mark(s, ST_PACK);
     return PDEREAD_OK;
@@ -959,6 +970,7 @@ static int dispatch_tc_fwd(int act, int nx, int nt, const TcFwdArgs& a, cudaStre
 
 // A forward launch of one network on whichever path its plan selected.
 struct FwdPlan {
+    int J;        // jet length (selects the packed weight layout of the CUDA-core path)
     bool tc;
     bool plain;   // J = 1: register-tiled kernel with its own weight layout
     int stash_pp; // plain kernel with a stash: points per lane of the stash tile (2 or 4)
@@ -969,6 +981,7 @@ struct FwdPlan {
 
 static int plan_forward(const NetDev& n, int J, bool allow_tc, Carver& cv, FwdPlan* p) {
     memset(p, 0, sizeof(*p));
+    p->J = J;
     // J = 1: the register-tiled plain-MLP kernel beats the tensor-core forward (5 x 100: 4.7 vs 6.0 ms per 2 M points)
     const bool prefer_plain = (J == 1) && tc_mode() != 2 && plain_fits(n, false);
     p->tc = allow_tc && !prefer_plain && tc_geometry(n, J, false, &p->geom);
@@ -984,7 +997,7 @@ static int plan_forward(const NetDev& n, int J, bool allow_tc, Carver& cv, FwdPl
 static int plan_pack(const NetDev& n, const FwdPlan& p, cudaStream_t s) {
     if (p.tc) return tc_pack(n, p.geom.mrows, p.geom.Kpad, p.geom.NB, p.geom.a_rs, p.geom.a_bytes, p.img, s);
     if (p.plain) return pack_plain(n, p.wt, s);
-    return pack(n, p.wt, nullptr, s);
+    return pack(n, p.J, p.wt, nullptr, s);
 }
 
 // `f` carries everything except wt_packed / num_tiles, which depend on the path.
@@ -1137,6 +1150,7 @@ static int plan_backward(const NetDev& n, int act, int nx, int nt, bool want_gin
     int rc;
     const int J = jet_len(nx, nt);
     memset(p, 0, sizeof(*p));
+    p->fwd.J = J;
     (void)want_gin;
     {
         // (128-point tiles need enough points to fill the GPU: below ~100 tiles per 148 SMs the 64-point kernel wins,
@@ -1164,9 +1178,9 @@ static int plan_backward_pack(const NetDev& n, const BwdPlan& p, cudaStream_t s)
     if (p.fwd.plain) {
         int rc = pack_plain(n, p.fwd.wt, s);
         if (rc) return rc;
-        return p.plain ? pack_plain(n, p.wn, s, 1) : pack(n, nullptr, p.wn, s);
+        return p.plain ? pack_plain(n, p.wn, s, 1) : pack(n, p.fwd.J, nullptr, p.wn, s);
     }
-    return pack(n, p.fwd.wt, p.wn, s);
+    return pack(n, p.fwd.J, p.fwd.wt, p.wn, s);
 }
 
 // `b` carries everything except the packed weights / tiles / grid, which depend on the path.

@@ -10,10 +10,20 @@ namespace pdr {
 constexpr int MAXL = PDEREAD_MAX_HIDDEN_LAYERS;
 constexpr int MAXD = PDEREAD_MAX_INPUT_DIM;
 
-// Thread mapping of the MLP-jet kernels: lane = collocation point, warp = chunk of TN neurons.
-constexpr int TN = 10;          // output neurons per thread in the layer products
-constexpr int TNP = 12;         // chunk length in the packed weights (keeps rows 16-byte aligned)
-constexpr int MAX_WARPS = 12;   // warps per CTA of the forward kernel (chunks beyond that are looped over)
+// Thread mappings of the layer products in the MLP-jet kernels (ProdTile in mlp_jet_kernels.cuh): a warp owns a
+// chunk of TN output neurons and the tile's points; the pair tile (J <= 4) splits the chunk into two halves of TH
+// neurons over the lane parity, the lane tile (J >= 5) gives every lane one point and all TN neurons.
+constexpr int TN = 10;          // output neurons per warp chunk
+constexpr int TH = 5;           // pair tile: neurons per thread (half chunk)
+constexpr int THP = 8;          // pair tile: half chunk padded to two 16-byte words in the packed weights
+constexpr int TNP_PAIR = 2 * THP;   // packed floats per chunk and row, pair tile: [half][THP]
+constexpr int TNP_LANE = 12;        // packed floats per chunk and row, lane tile (keeps rows 16-byte aligned)
+constexpr int TNP = TNP_PAIR;       // workspace sizing: the larger of the two
+#ifndef PDR_PAIR_MAXJ
+#define PDR_PAIR_MAXJ 4             // longest jet that uses the pair tile (A/B builds: PDR_EXTRA_CFLAGS=-DPDR_PAIR_MAXJ=..)
+#endif
+inline bool use_pair_map(int J) { return J <= PDR_PAIR_MAXJ; }    // UsePairMap<J>
+constexpr int MAX_WARPS = 16;   // warps per CTA of the forward kernel (chunks beyond that are looped over)
 constexpr int BWD_WIDE_WARPS = 16;   // warps of the reverse kernel when only one CTA fits an SM
 
 // points per lane as a function of the jet length J = 1 + NX + NT
@@ -63,7 +73,7 @@ struct GradLayout {
 
 struct FwdArgs {
     NetDev net;
-    const float* wt_packed;   // [L-1][W][NC*TNP], wt[l][k][c*TNP+n] = W_{l+1}[c*TN+n][k]
+    const float* wt_packed;   // [L-1][W][NC*WROW] transposed weights in the layout of the kernel's ProdTile (pack_weights_kernel)
     const float* in;          // [M][din]
     long long M;
     long long num_tiles;
@@ -84,7 +94,7 @@ struct FwdArgs {
 struct BwdArgs {
     NetDev net;
     GradLayout lay;
-    const float* wn_packed;   // [L-1][W][NC*TNP], wn[l][i][c*TNP+n] = W_{l+1}[i][c*TN+n]
+    const float* wn_packed;   // [L-1][W][NC*WROW] native weights in the layout of the kernel's ProdTile
     const float* in;          // [M][din]
     long long M;
     long long num_tiles;

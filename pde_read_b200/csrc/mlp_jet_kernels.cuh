@@ -73,80 +73,186 @@ __device__ __forceinline__ void row_load(const float* p, float* z) {
     }
 }
 
-// One k-step of a layer product, acc[q][j][n] += h[q][j] * w[n] for the TN weights of this warp's chunk,
-// issued as packed fma.rn.f32x2 (two FMAs per instruction, same rounding as fmaf): the weights arrive as
-// aligned pairs from the 16-byte loads, the activation is duplicated into a pair.
-template <int PPL, int J>
-__device__ __forceinline__ void product_step(float2 (&acc)[PPL][J][TN / 2], const float* __restrict__ hk,
-                                             const float* __restrict__ wk) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(wk));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(wk) + 1);
-    const float4 b2 = __ldg(reinterpret_cast<const float4*>(wk) + 2);
-    const float2 bw[TNP / 2] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
-                                make_float2(b1.z, b1.w), make_float2(b2.x, b2.y), make_float2(b2.z, b2.w)};
+// ---- register tiles of the layer products ----------------------------------------------------------------------
+// Two thread mappings, chosen by the jet length (UsePairMap): both give a warp a chunk of TN = 10 output neurons and
+// all points of the tile, both keep 10 (neuron, point) jets per thread and issue packed fma.rn.f32x2 (SASS FFMA2:
+// two FMAs per instruction, same rounding as fmaf, one operand a broadcast scalar).
+//   PairTile (J <= 4): lane = 2 a + b; b picks a half of the chunk (TH = 5 neurons), a a slot of points (a, a + 16, ..).
+//     Per k-step: the 5 weights of the half (LDG.128 + LDG.32, two addresses per warp) and one 8- / 16-byte row
+//     segment per point (16 distinct, contiguous); FFMA2 pairs are jet coefficients (2t, 2t+1) of a point, for odd J
+//     the last coefficients of two points; the weight is the scalar operand.
+//   LaneTile (J >= 5): lane = point, 10 neurons per thread.  Per k-step: three warp-uniform LDG.128 (10 weights as
+//     pairs) and the J coefficients of the lane's point; FFMA2 pairs are neighbouring neurons, the activation is the
+//     scalar operand.
+// Measured on one B200, forward-U of the bench configurations (ms): J = 4 (C2, 100 k points) pair 0.265 / lane 0.320;
+// J = 3 (C5, 10 M) 21.0 / 21.8; J = 5 (C3, 1 M) 4.15 / 3.71; J = 6 (C4, 524 k) 9.3 / 8.35 -- the long jets need more
+// row loads per k-step in the pair tile (6 LDS.64 against 3) and lose.
+template <int J>
+struct UsePairMap {
+    static constexpr bool v = (J <= PDR_PAIR_MAXJ);
+};
+
+// the J coefficients of one point from a row with point stride JP (p is 4 JP-byte aligned)
+template <int J, int JP>
+__device__ __forceinline__ void point_load(const float* p, float* z) {
+    float t[JP];
+    if constexpr (JP % 4 == 0) {
 #pragma unroll
-    for (int q = 0; q < PPL; ++q) {
-        float hv[J];
-        row_load<J>(hk + q * 32 * J, hv);
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const float2 a2 = make_float2(hv[j], hv[j]);
-#pragma unroll
-            for (int n = 0; n < TN / 2; ++n) acc[q][j][n] = __ffma2_rn(a2, bw[n], acc[q][j][n]);
+        for (int j = 0; j < JP; j += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(p + j);
+            t[j] = v.x; t[j + 1] = v.y; t[j + 2] = v.z; t[j + 3] = v.w;
         }
+    } else if constexpr (JP % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < JP; j += 2) {
+            const float2 v = *reinterpret_cast<const float2*>(p + j);
+            t[j] = v.x; t[j + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < JP; ++j) t[j] = p[j];
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) z[j] = t[j];
+}
+template <int J, int JP>
+__device__ __forceinline__ void point_store(float* p, const float* z) {
+    float t[JP];
+#pragma unroll
+    for (int j = 0; j < JP; ++j) t[j] = (j < J) ? z[j] : 0.f;
+    if constexpr (JP % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < JP; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
+    } else if constexpr (JP % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < JP; j += 2) *reinterpret_cast<float2*>(p + j) = make_float2(t[j], t[j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < JP; ++j) p[j] = t[j];
     }
 }
 
-// The whole reduction of one layer product for this warp's chunk.  For the plain MLP (J = 1: 10 FFMA2 per point
-// and step against 3 weight loads) it is software-pipelined by one k-step: the weights and the activations of step
-// k+1 are requested before the FMAs of step k are issued (forward-N at C2 0.171 -> 0.144 ms).
+template <bool PAIR, int PPL, int J>
+struct ProdTile;
+
 template <int PPL, int J>
-__device__ __forceinline__ void product_loop(float2 (&acc)[PPL][J][TN / 2], const float* __restrict__ h, int HS,
-                                             const float* __restrict__ w, int wstride, int W) {
-    if constexpr (J > 1) {
-        // long jets: 20+ FFMA2 per step and 40+ accumulators; the explicit pipeline costs more (register moves,
-        // pointer selects) than it hides -- measured +8 % (forward) .. +14 % (reverse) at J = 4, +16 % at J = 6
-#pragma unroll 2
-        for (int k = 0; k < W; ++k) {
-            product_step<PPL, J>(acc, h, w);
-            w += wstride;
-            h += HS;
-        }
-        return;
+struct ProdTile<true, PPL, J> {
+    static constexpr int NPT = TH;              // neurons per thread
+    static constexpr int QP = 2 * PPL;          // points per thread
+    static constexpr int WROW = TNP_PAIR;       // packed floats per chunk and k
+    // point stride of the forward kernel's rows: odd jet lengths padded to an even stride (8- / 16-byte row accesses;
+    // J = 3 at C5: 21.0 ms against 22.4 unpadded).  The reverse kernel keeps J: its weight-gradient tiles reduce over
+    // whole rows.
+    static constexpr int JP_FWD = (J == 1) ? 1 : ((J + 1) & ~1);
+    static constexpr int JE = J / 2;
+    float2 e[TH][QP][JE > 0 ? JE : 1];
+    float2 o[TH][QP / 2];
+    static __device__ __forceinline__ int neuron(int lane, int c, int n) { return c * TN + (lane & 1) * TH + n; }
+    static __device__ __forceinline__ int point(int lane, int q) { return (lane >> 1) + 16 * q; }
+    static __device__ __forceinline__ int wofs(int lane, int c) { return c * TNP_PAIR + (lane & 1) * THP; }
+    __device__ __forceinline__ float get(int n, int q, int j) const {
+        if (j < 2 * JE) return (j & 1) ? e[n][q][j >> 1].y : e[n][q][j >> 1].x;
+        return (q & 1) ? o[n][q >> 1].y : o[n][q >> 1].x;
     }
-    float4 b0 = __ldg(reinterpret_cast<const float4*>(w));
-    float4 b1 = __ldg(reinterpret_cast<const float4*>(w) + 1);
-    float4 b2 = __ldg(reinterpret_cast<const float4*>(w) + 2);
-    float hv[PPL][J];
-#pragma unroll
-    for (int q = 0; q < PPL; ++q) row_load<J>(h + q * 32 * J, hv[q]);
-#pragma unroll 2
-    for (int k = 0; k < W; ++k) {
-        if (k + 1 < W) {           // the last step re-reads its own operands (no branch around the loads)
-            w += wstride;
-            h += HS;
+    __device__ __forceinline__ void set(int n, int q, int j, float v) {
+        if (j < 2 * JE) {
+            if (j & 1) e[n][q][j >> 1].y = v; else e[n][q][j >> 1].x = v;
+        } else {
+            if (q & 1) o[n][q >> 1].y = v; else o[n][q >> 1].x = v;
         }
-        const float4 n0 = __ldg(reinterpret_cast<const float4*>(w));
-        const float4 n1 = __ldg(reinterpret_cast<const float4*>(w) + 1);
-        const float4 n2 = __ldg(reinterpret_cast<const float4*>(w) + 2);
-        float hn[PPL][J];
+    }
+    __device__ __forceinline__ void zero() {
 #pragma unroll
-        for (int q = 0; q < PPL; ++q) row_load<J>(h + q * 32 * J, hn[q]);
-        const float2 bw[TNP / 2] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
-                                    make_float2(b1.z, b1.w), make_float2(b2.x, b2.y), make_float2(b2.z, b2.w)};
+        for (int n = 0; n < TH; ++n) {
 #pragma unroll
-        for (int q = 0; q < PPL; ++q)
+            for (int q = 0; q < QP; ++q)
+#pragma unroll
+                for (int t = 0; t < JE; ++t) e[n][q][t] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int s = 0; s < QP / 2; ++s) o[n][s] = make_float2(0.f, 0.f);
+        }
+    }
+    // one k-step: acc[n][q][j] += w[n] h[q][j].  hk: row k of the activation buffer at this thread's first point,
+    // wk: this thread's weights of row k
+    template <int JP>
+    __device__ __forceinline__ void step(const float* __restrict__ hk, const float* __restrict__ wk) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wk));
+        const float w5 = __ldg(wk + 4);
+        const float wv[TH] = {w4.x, w4.y, w4.z, w4.w, w5};
+        float hv[QP][J];
+#pragma unroll
+        for (int q = 0; q < QP; ++q) point_load<J, JP>(hk + 16 * q * JP, hv[q]);
+#pragma unroll
+        for (int q = 0; q < QP; ++q)
+#pragma unroll
+            for (int t = 0; t < JE; ++t) {
+                const float2 h2 = make_float2(hv[q][2 * t], hv[q][2 * t + 1]);
+#pragma unroll
+                for (int n = 0; n < TH; ++n) e[n][q][t] = __ffma2_rn(make_float2(wv[n], wv[n]), h2, e[n][q][t]);
+            }
+        if constexpr (J & 1) {
+#pragma unroll
+            for (int s = 0; s < QP / 2; ++s) {
+                const float2 h2 = make_float2(hv[2 * s][J - 1], hv[2 * s + 1][J - 1]);
+#pragma unroll
+                for (int n = 0; n < TH; ++n) o[n][s] = __ffma2_rn(make_float2(wv[n], wv[n]), h2, o[n][s]);
+            }
+        }
+    }
+};
+
+template <int PPL, int J>
+struct ProdTile<false, PPL, J> {
+    static constexpr int NPT = TN;
+    static constexpr int QP = PPL;
+    static constexpr int WROW = TNP_LANE;
+    static constexpr int JP_FWD = J;
+    float2 a[QP][J][TN / 2];
+    static __device__ __forceinline__ int neuron(int, int c, int n) { return c * TN + n; }
+    static __device__ __forceinline__ int point(int lane, int q) { return lane + 32 * q; }
+    static __device__ __forceinline__ int wofs(int, int c) { return c * TNP_LANE; }
+    __device__ __forceinline__ float get(int n, int q, int j) const { return (n & 1) ? a[q][j][n >> 1].y : a[q][j][n >> 1].x; }
+    __device__ __forceinline__ void set(int n, int q, int j, float v) {
+        if (n & 1) a[q][j][n >> 1].y = v; else a[q][j][n >> 1].x = v;
+    }
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int q = 0; q < QP; ++q)
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+#pragma unroll
+                for (int n = 0; n < TN / 2; ++n) a[q][j][n] = make_float2(0.f, 0.f);
+    }
+    template <int JP>
+    __device__ __forceinline__ void step(const float* __restrict__ hk, const float* __restrict__ wk) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(wk));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(wk) + 1);
+        const float4 b2 = __ldg(reinterpret_cast<const float4*>(wk) + 2);
+        const float2 bw[TNP_LANE / 2] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                         make_float2(b1.z, b1.w), make_float2(b2.x, b2.y), make_float2(b2.z, b2.w)};
+#pragma unroll
+        for (int q = 0; q < QP; ++q) {
+            float hv[J];
+            point_load<J, JP>(hk + q * 32 * JP, hv);
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                const float2 a2 = make_float2(hv[q][j], hv[q][j]);
+                const float2 a2 = make_float2(hv[j], hv[j]);
 #pragma unroll
-                for (int n = 0; n < TN / 2; ++n) acc[q][j][n] = __ffma2_rn(a2, bw[n], acc[q][j][n]);
+                for (int n = 0; n < TN / 2; ++n) a[q][j][n] = __ffma2_rn(a2, bw[n], a[q][j][n]);
             }
-        b0 = n0; b1 = n1; b2 = n2;
-#pragma unroll
-        for (int q = 0; q < PPL; ++q)
-#pragma unroll
-            for (int j = 0; j < J; ++j) hv[q][j] = hn[q][j];
+        }
+    }
+};
+
+// The whole reduction of one layer product for this thread's register tile.
+template <int JP, class Tile>
+__device__ __forceinline__ void product_loop(Tile& acc, const float* __restrict__ h, int HS,
+                                             const float* __restrict__ w, int wstride, int W) {
+#pragma unroll 2
+    for (int k = 0; k < W; ++k) {
+        acc.template step<JP>(h, w);
+        w += wstride;
+        h += HS;
     }
 }
 
@@ -206,13 +312,16 @@ __device__ __forceinline__ void input_layer_jet(const NetDev& net, const float* 
 // =============================================================================================
 // forward
 // =============================================================================================
-// PPL = points per lane: PointsPerLane<J> (the tile the reverse kernel and the stash use), or FWD_ONLY_PPL_J1 for
-// forward-only calls of the plain MLP (J = 1), whose 3 weight loads per k-step then feed 20 FFMA2 instead of 10.
+// PPL = points per lane on average (tile = 32 PPL points): PointsPerLane<J> (the tile the reverse kernel and the
+// stash use), or FWD_ONLY_PPL_J1 for forward-only calls of the plain MLP (J = 1).
 template <int ACT, int NX, int NT, bool STASH, int PPL>
 __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_kernel(const FwdArgs a) {
     constexpr int J = 1 + NX + NT;
+    using Tile = ProdTile<UsePairMap<J>::v, PPL, J>;
+    constexpr int JP = Tile::JP_FWD;
     constexpr int TP = 32 * PPL;
-    constexpr int HS = J * TP + 4;
+    constexpr int QP = Tile::QP, NPT = Tile::NPT;
+    constexpr int HS = JP * TP + 4;
 
     extern __shared__ __align__(16) float smem[];
     const NetDev& net = a.net;
@@ -236,9 +345,9 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
         }
         __syncthreads();
 
-        float part[PPL][J];
+        float part[QP][J];
 #pragma unroll
-        for (int q = 0; q < PPL; ++q)
+        for (int q = 0; q < QP; ++q)
 #pragma unroll
             for (int j = 0; j < J; ++j) part[q][j] = 0.f;
 
@@ -250,21 +359,22 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
         load_ab<ACT>(net, 0, ab);
         for (int c = warp; c < NC; c += nwarps) {
 #pragma unroll 1
-            for (int n = 0; n < TN; ++n) {
-                const int i = c * TN + n;
-                if (i >= W) break;
-                const float wo = (L == 1) ? __ldg(wout + i) : 0.f;
+            for (int n = 0; n < NPT; ++n) {
+                const int i = Tile::neuron(lane, c, n);
+                if (i < W) {
+                    const float wo = (L == 1) ? __ldg(wout + i) : 0.f;
 #pragma unroll
-                for (int q = 0; q < PPL; ++q) {
-                    const int pt = q * 32 + lane;
-                    float z[J], y[J];
-                    input_layer_jet<NX, NT>(net, IN, TP, i, pt, z);
-                    act_fwd<ACT, NX, NT, float>(z, ab, y);
-                    if (L == 1) {
+                    for (int q = 0; q < QP; ++q) {
+                        const int pt = Tile::point(lane, q);
+                        float z[J], y[J];
+                        input_layer_jet<NX, NT>(net, IN, TP, i, pt, z);
+                        act_fwd<ACT, NX, NT, float>(z, ab, y);
+                        if (L == 1) {
 #pragma unroll
-                        for (int j = 0; j < J; ++j) part[q][j] = fmaf(wo, y[j], part[q][j]);
-                    } else {
-                        stash_store<J>(Hin + (size_t)i * HS + pt * J, y);
+                            for (int j = 0; j < J; ++j) part[q][j] = fmaf(wo, y[j], part[q][j]);
+                        } else {
+                            point_store<J, JP>(Hin + (size_t)i * HS + pt * JP, y);
+                        }
                     }
                 }
             }
@@ -273,45 +383,32 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
 
         // ---- hidden layers 1 .. L-1 ------------------------------------------------------
         for (int l = 1; l < L; ++l) {
-            const float* wp = a.wt_packed + (size_t)(l - 1) * W * NC * TNP;
+            const float* wp = a.wt_packed + (size_t)(l - 1) * W * NC * Tile::WROW;
             const float* bias = net.b[l];
             const bool last = (l == L - 1);
             load_ab<ACT>(net, l, ab);
             for (int c = warp; c < NC; c += nwarps) {
-                float2 acc2[PPL][J][TN / 2];
+                Tile acc;
+                acc.zero();
 #pragma unroll
-                for (int n = 0; n < TN; n += 2) {
-                    const int i = c * TN + n;
-                    const float bv0 = (i < W) ? __ldg(bias + i) : 0.f, bv1 = (i + 1 < W) ? __ldg(bias + i + 1) : 0.f;
+                for (int n = 0; n < NPT; ++n) {
+                    const int i = Tile::neuron(lane, c, n);
+                    const float bv = (i < W) ? __ldg(bias + i) : 0.f;
 #pragma unroll
-                    for (int q = 0; q < PPL; ++q) {
-                        acc2[q][0][n / 2] = make_float2(bv0, bv1);
-#pragma unroll
-                        for (int j = 1; j < J; ++j) acc2[q][j][n / 2] = make_float2(0.f, 0.f);
-                    }
+                    for (int q = 0; q < QP; ++q) acc.set(n, q, 0, bv);
                 }
-                product_loop<PPL, J>(acc2, Hin + lane * J, HS, wp + c * TNP, NC * TNP, W);
-                float acc[PPL][J][TN];
+                product_loop<JP>(acc, Hin + Tile::point(lane, 0) * JP, HS, wp + Tile::wofs(lane, c), NC * Tile::WROW, W);
 #pragma unroll
-                for (int q = 0; q < PPL; ++q)
-#pragma unroll
-                    for (int j = 0; j < J; ++j)
-#pragma unroll
-                        for (int n = 0; n < TN / 2; ++n) {
-                            acc[q][j][2 * n] = acc2[q][j][n].x;
-                            acc[q][j][2 * n + 1] = acc2[q][j][n].y;
-                        }
-#pragma unroll
-                for (int n = 0; n < TN; ++n) {
-                    const int i = c * TN + n;
+                for (int n = 0; n < NPT; ++n) {
+                    const int i = Tile::neuron(lane, c, n);
                     if (i < W) {
                         const float wo = last ? __ldg(wout + i) : 0.f;
 #pragma unroll
-                        for (int q = 0; q < PPL; ++q) {
-                            const int pt = q * 32 + lane;
+                        for (int q = 0; q < QP; ++q) {
+                            const int pt = Tile::point(lane, q);
                             float z[J], y[J];
 #pragma unroll
-                            for (int j = 0; j < J; ++j) z[j] = acc[q][j][n];
+                            for (int j = 0; j < J; ++j) z[j] = acc.get(n, q, j);
                             act_fwd<ACT, NX, NT, float>(z, ab, y);
                             if (STASH) {
                                 if (ACT == ACT_TANH) z[0] = y[0];       // see "rows of the reverse pass"
@@ -321,7 +418,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
 #pragma unroll
                                 for (int j = 0; j < J; ++j) part[q][j] = fmaf(wo, y[j], part[q][j]);
                             } else {
-                                stash_store<J>(Hout + (size_t)i * HS + pt * J, y);
+                                point_store<J, JP>(Hout + (size_t)i * HS + pt * JP, y);
                             }
                         }
                     }
@@ -331,11 +428,19 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
             float* t = Hin; Hin = Hout; Hout = t;
         }
 
-        // ---- output layer: reduce the per-warp partial dot products -----------------------
+        // ---- output layer: (pair tile: the two halves of a chunk meet in a lane pair,) the chunks in shared memory
 #pragma unroll
-        for (int q = 0; q < PPL; ++q)
+        for (int q = 0; q < QP; ++q)
 #pragma unroll
-            for (int j = 0; j < J; ++j) RED[(warp * J + j) * TP + q * 32 + lane] = part[q][j];
+            for (int j = 0; j < J; ++j) {
+                float v = part[q][j];
+                if constexpr (UsePairMap<J>::v) {
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    if ((lane & 1) == 0) RED[(warp * J + j) * TP + Tile::point(lane, q)] = v;
+                } else {
+                    RED[(warp * J + j) * TP + Tile::point(lane, q)] = v;
+                }
+            }
         __syncthreads();
         const float bout = __ldg(net.b[L]);
         for (int idx = threadIdx.x; idx < J * TP; idx += blockDim.x) {
@@ -510,6 +615,8 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
     constexpr int J = 1 + NX + NT;
     constexpr int PPL = PointsPerLane<J>::v;
     constexpr int TP = 32 * PPL;
+    using Tile = ProdTile<UsePairMap<J>::v, PPL, J>;
+    constexpr int QP = Tile::QP, NPT = Tile::NPT;
     constexpr int HS = J * TP + 4;
 
     extern __shared__ __align__(16) float smem[];
@@ -659,30 +766,25 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
 #pragma unroll
             for (int t = 0; t < 7; ++t) abbar[t] = 0.f;
             const float* st_z = a.stash + ((size_t)tile * (L - 1) + (lv > 0 ? lv - 1 : 0)) * W * (J * TP);
-            const float* wp = a.wn_packed + (size_t)(l - 1) * W * NC * TNP;
+            const float* wp = a.wn_packed + (size_t)(l - 1) * W * NC * Tile::WROW;
             for (int c = warp; c < NC; c += nwarps) {
-                float2 acc2[PPL][J][TN / 2];
-#pragma unroll
-                for (int q = 0; q < PPL; ++q)
-#pragma unroll
-                    for (int j = 0; j < J; ++j)
-#pragma unroll
-                        for (int n = 0; n < TN / 2; ++n) acc2[q][j][n] = make_float2(0.f, 0.f);
-                product_loop<PPL, J>(acc2, Zb + lane * J, HS, wp + c * TNP, NC * TNP, W);
+                Tile acc;
+                acc.zero();
+                product_loop<J>(acc, Zb + Tile::point(lane, 0) * J, HS, wp + Tile::wofs(lane, c), NC * Tile::WROW, W);
                 if (fused) {
 #pragma unroll
-                    for (int n = 0; n < TN; ++n) {
-                        const int k = c * TN + n;
+                    for (int n = 0; n < NPT; ++n) {
+                        const int k = Tile::neuron(lane, c, n);
                         if (k < W) {
 #pragma unroll
-                            for (int q = 0; q < PPL; ++q) {
-                                const int pt = q * 32 + lane;
+                            for (int q = 0; q < QP; ++q) {
+                                const int pt = Tile::point(lane, q);
                                 float z[J], y[J], ybar[J], zbar[J];
                                 if (lv == 0) input_layer_row<ACT, NX, NT>(net, IN, TP, k, pt, z);
                                 else         stash_load<J>(st_z + (size_t)k * (J * TP) + pt * J, z);
 #pragma unroll
                                 for (int j = 0; j < J; ++j) {
-                                    ybar[j] = (n & 1) ? acc2[q][j][n / 2].y : acc2[q][j][n / 2].x;
+                                    ybar[j] = acc.get(n, q, j);
                                     y[j] = 0.f;
                                 }
                                 if (VJP_FROM_Y<ACT>::v) row_load<J>(Yb + (size_t)k * HS + pt * J, y);
@@ -693,15 +795,15 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                     }
                 } else {
 #pragma unroll
-                    for (int n = 0; n < TN; ++n) {
-                        const int k = c * TN + n;
+                    for (int n = 0; n < NPT; ++n) {
+                        const int k = Tile::neuron(lane, c, n);
                         if (k < W) {
 #pragma unroll
-                            for (int q = 0; q < PPL; ++q) {
+                            for (int q = 0; q < QP; ++q) {
                                 float ybar[J];
 #pragma unroll
-                                for (int j = 0; j < J; ++j) ybar[j] = (n & 1) ? acc2[q][j][n / 2].y : acc2[q][j][n / 2].x;
-                                stash_store<J>(Yb + (size_t)k * HS + (q * 32 + lane) * J, ybar);
+                                for (int j = 0; j < J; ++j) ybar[j] = acc.get(n, q, j);
+                                stash_store<J>(Yb + (size_t)k * HS + Tile::point(lane, q) * J, ybar);
                             }
                         }
                     }

@@ -66,6 +66,15 @@ def _check_tensor(t: torch.Tensor, what: str, dtype=torch.float32) -> torch.Tens
     return t.contiguous()
 
 
+def _check_param(t: torch.Tensor, what: str) -> torch.Tensor:
+    """Network parameters are passed by pointer and the pointer table is cached (_fill_net): a non-contiguous
+    parameter would be copied once and the kernels would keep reading the stale copy after an in-place
+    optimiser step, so it is refused instead."""
+    if not t.is_contiguous():
+        raise PdereadError("%s must be contiguous (parameters are passed to the kernels by pointer)" % what)
+    return _check_tensor(t, what)
+
+
 _NET_CACHE: dict = {}
 
 
@@ -96,8 +105,8 @@ def _fill_net_uncached(spec: NetSpec, tensors: Sequence[torch.Tensor]) -> Tuple[
     keep = []
     L = spec.num_hidden
     for i in range(L + 1):
-        w = _check_tensor(tensors[2 * i].detach(), "Layers.%d.weight" % i)
-        b = _check_tensor(tensors[2 * i + 1].detach(), "Layers.%d.bias" % i)
+        w = _check_param(tensors[2 * i].detach(), "Layers.%d.weight" % i)
+        b = _check_param(tensors[2 * i + 1].detach(), "Layers.%d.bias" % i)
         exp_w = (spec.width if i < L else 1, spec.input_dim if i == 0 else spec.width)
         if tuple(w.shape) != exp_w or b.numel() != exp_w[0]:
             raise PdereadError("Layers.%d has shape %s / %s, expected %s" % (i, tuple(w.shape), tuple(b.shape), exp_w))
@@ -107,8 +116,8 @@ def _fill_net_uncached(spec: NetSpec, tensors: Sequence[torch.Tensor]) -> Tuple[
     if spec.activation == "Rational":
         base = 2 * (L + 1)
         for i in range(L):
-            a = _check_tensor(tensors[base + 2 * i].detach(), "Activation_Functions.%d.a" % i)
-            b = _check_tensor(tensors[base + 2 * i + 1].detach(), "Activation_Functions.%d.b" % i)
+            a = _check_param(tensors[base + 2 * i].detach(), "Activation_Functions.%d.a" % i)
+            b = _check_param(tensors[base + 2 * i + 1].detach(), "Activation_Functions.%d.b" % i)
             if a.numel() != 4 or b.numel() != 3:
                 raise PdereadError("Rational coefficients must have 4 and 3 entries")
             keep += [a, b]
