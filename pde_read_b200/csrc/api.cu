@@ -101,10 +101,31 @@ size_t fwd_smem_bytes_tile(int W, int din, int J, int nwarps, int TP) {
     return sizeof(float) * ((size_t)2 * W * HS + (size_t)din * TP + (size_t)nwarps * J * TP);
 }
 size_t fwd_smem_bytes(int W, int din, int J, int nwarps) { return fwd_smem_bytes_tile(W, din, J, nwarps, tile_points(J)); }
-size_t bwd_smem_bytes(int W, int L, int din, int J) {
+static size_t bwd_smem_bytes_base(int W, int L, int din, int J) {
     const int TP = tile_points(J), HS = h_stride(J);
     const size_t ns = (((size_t)L * W + 1 + (size_t)W * din + W + 7 * L + 3) & ~(size_t)3) + HS;   // + the ones row
     return sizeof(float) * ((size_t)2 * W * HS + (size_t)2 * din * TP + (size_t)J * TP + ns);
+}
+static size_t bwd_wstage_bytes(int W, int J) {
+    const int NC = (W + TN - 1) / TN;
+    return sizeof(float) * (size_t)W * NC * (use_pair_map(J) ? TNP_PAIR : TNP_LANE);
+}
+bool bwd_stage_weights(int W, int L, int din, int J) {
+    static int mode = -1;     // PDEREAD_BWD_STAGE=0|1 overrides the rule below (A/B measurements)
+    if (mode < 0) {
+        const char* e = getenv("PDEREAD_BWD_STAGE");
+        mode = !e ? 2 : (e[0] == '1' ? 1 : 0);
+    }
+    if (!mode || L < 2) return false;
+    const size_t sm = 227 * 1024;
+    const size_t base = bwd_smem_bytes_base(W, L, din, J) + 1024, staged = base + bwd_wstage_bytes(W, J) + 16;
+    if (staged > sm) return false;
+    // default: only where the copy does not cost a resident CTA (C4: -10 % on the reverse kernel; C2 / C3 would drop
+    // from 4 / 3 CTAs per SM to 3 / 2 and lose 11 / 15 %)
+    return mode == 1 || sm / staged == sm / base;
+}
+size_t bwd_smem_bytes(int W, int L, int din, int J) {
+    return bwd_smem_bytes_base(W, L, din, J) + (bwd_stage_weights(W, L, din, J) ? bwd_wstage_bytes(W, J) + 16 : 0);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -180,6 +180,7 @@ inline int h_stride(int J) { return J * tile_points(J) + 4; }
 size_t fwd_smem_bytes(int W, int din, int J, int nwarps);
 size_t fwd_smem_bytes_tile(int W, int din, int J, int nwarps, int TP);   // for an explicit tile of TP points
 size_t bwd_smem_bytes(int W, int L, int din, int J);
+bool bwd_stage_weights(int W, int L, int din, int J);   // reverse kernel: stage the layer's weights in shared memory
 int block_warps(int W);
 int bwd_block_warps(int W, int L, int din, int J);
 

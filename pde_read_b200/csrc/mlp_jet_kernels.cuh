@@ -37,6 +37,15 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+                 :
+                 : "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 template <int ACT>
 __device__ __forceinline__ void load_ab(const NetDev& net, int l, float* ab) {
     if (ACT == ACT_RATIONAL) {
@@ -174,10 +183,10 @@ struct ProdTile<true, PPL, J> {
     }
     // one k-step: acc[n][q][j] += w[n] h[q][j].  hk: row k of the activation buffer at this thread's first point,
     // wk: this thread's weights of row k
-    template <int JP>
+    template <int JP, bool WS>
     __device__ __forceinline__ void step(const float* __restrict__ hk, const float* __restrict__ wk) {
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wk));
-        const float w5 = __ldg(wk + 4);
+        const float4 w4 = WS ? *reinterpret_cast<const float4*>(wk) : __ldg(reinterpret_cast<const float4*>(wk));
+        const float w5 = WS ? wk[4] : __ldg(wk + 4);
         const float wv[TH] = {w4.x, w4.y, w4.z, w4.w, w5};
         float hv[QP][J];
 #pragma unroll
@@ -223,11 +232,12 @@ struct ProdTile<false, PPL, J> {
 #pragma unroll
                 for (int n = 0; n < TN / 2; ++n) a[q][j][n] = make_float2(0.f, 0.f);
     }
-    template <int JP>
+    template <int JP, bool WS>
     __device__ __forceinline__ void step(const float* __restrict__ hk, const float* __restrict__ wk) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(wk));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(wk) + 1);
-        const float4 b2 = __ldg(reinterpret_cast<const float4*>(wk) + 2);
+        const float4* w4p = reinterpret_cast<const float4*>(wk);
+        const float4 b0 = WS ? w4p[0] : __ldg(w4p);
+        const float4 b1 = WS ? w4p[1] : __ldg(w4p + 1);
+        const float4 b2 = WS ? w4p[2] : __ldg(w4p + 2);
         const float2 bw[TNP_LANE / 2] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
                                          make_float2(b1.z, b1.w), make_float2(b2.x, b2.y), make_float2(b2.z, b2.w)};
 #pragma unroll
@@ -244,13 +254,14 @@ struct ProdTile<false, PPL, J> {
     }
 };
 
-// The whole reduction of one layer product for this thread's register tile.
-template <int JP, class Tile>
+// The whole reduction of one layer product for this thread's register tile.  WS: the weights were staged in shared
+// memory (plain loads), else they come through the read-only path.
+template <int JP, bool WS, class Tile>
 __device__ __forceinline__ void product_loop(Tile& acc, const float* __restrict__ h, int HS,
                                              const float* __restrict__ w, int wstride, int W) {
 #pragma unroll 2
     for (int k = 0; k < W; ++k) {
-        acc.template step<JP>(h, w);
+        acc.template step<JP, WS>(h, w);
         w += wstride;
         h += HS;
     }
@@ -314,6 +325,9 @@ __device__ __forceinline__ void input_layer_jet(const NetDev& net, const float* 
 // =============================================================================================
 // PPL = points per lane on average (tile = 32 PPL points): PointsPerLane<J> (the tile the reverse kernel and the
 // stash use), or FWD_ONLY_PPL_J1 for forward-only calls of the plain MLP (J = 1).
+// (Measured and dropped: a single activation buffer updated in place -- outputs wait in their accumulator registers
+// for a barrier, then replace the layer below.  It halves the shared memory, but costs a barrier per layer and, where
+// it buys a second CTA (width 100, J = 6), a 96-register cap: C4 forward 8.59 ms against 8.28, C3 4.18 against 3.72.)
 template <int ACT, int NX, int NT, bool STASH, int PPL>
 __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_kernel(const FwdArgs a) {
     constexpr int J = 1 + NX + NT;
@@ -397,7 +411,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
 #pragma unroll
                     for (int q = 0; q < QP; ++q) acc.set(n, q, 0, bv);
                 }
-                product_loop<JP>(acc, Hin + Tile::point(lane, 0) * JP, HS, wp + Tile::wofs(lane, c), NC * Tile::WROW, W);
+                product_loop<JP, false>(acc, Hin + Tile::point(lane, 0) * JP, HS, wp + Tile::wofs(lane, c), NC * Tile::WROW, W);
 #pragma unroll
                 for (int n = 0; n < NPT; ++n) {
                     const int i = Tile::neuron(lane, c, n);
@@ -636,6 +650,10 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
     const int sab = swout + W;                 // rational coefficients [L][7]
     const int NS = sab + 7 * L;
     float* ONES = SACC + ((NS + 3) & ~3);      // [HS] 1 at the order-0 coefficient of every point, 0 elsewhere (bias column)
+    // a.aux != 0: the weights of the matrix below are copied into shared memory (cp.async) while the weight-gradient
+    // tiles of phase (b) run, and the product of phase (c) reads them from there
+    float* WSB = ONES + ((HS + 3) & ~3);       // [W][NC * WROW]
+    const bool stage = a.aux != 0;
 
     // activation-only phases: one work item = G neurons; blocks with more warps than neuron chunks (wide
     // networks, one CTA per SM) hand out single neurons so that all warps take part
@@ -748,6 +766,12 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
         // ---- hidden layers below, top down.  At the head of a trip Zb = zbar^{lv+1}, Yb = y^{lv}.
         for (int lv = L - 2; lv >= 0; --lv) {
             const int l = lv + 1;   // weight matrix between hidden layers lv and lv+1
+            if (stage) {
+                const float4* src = reinterpret_cast<const float4*>(a.wn_packed + (size_t)(l - 1) * W * NC * Tile::WROW);
+                float4* dst = reinterpret_cast<float4*>(WSB);
+                for (int i = threadIdx.x; i < W * NC * Tile::WROW / 4; i += blockDim.x) cp_async16(dst + i, src + i);
+                cp_async_commit();
+            }
             // (b) weight gradient of matrix l:  gW[i][k] += sum_r Zb[i][r] Yb[k][r]  (+ bias column)
             {
                 float* gw = gp + a.lay.off_w[l];
@@ -755,6 +779,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                 else if (a.wg_mode == 1) wgrad_tiles<5, 3>(Zb, Yb, ONES, W, HS, J * TP, gw, SACC + l * W);
                 else                     wgrad_tiles<5, 2>(Zb, Yb, ONES, W, HS, J * TP, gw, SACC + l * W);
             }
+            if (stage) cp_async_wait_all();
             __syncthreads();
             // (c) ybar^{lv}[k] = sum_i W_l[i][k] Zb[i].  Fused blocks (one warp per neuron chunk): ybar stays in the
             //     registers of the thread that owns (k, point) and the activation VJP runs in the same thread,
@@ -770,7 +795,10 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
             for (int c = warp; c < NC; c += nwarps) {
                 Tile acc;
                 acc.zero();
-                product_loop<J>(acc, Zb + Tile::point(lane, 0) * J, HS, wp + Tile::wofs(lane, c), NC * Tile::WROW, W);
+                if (stage) product_loop<J, true>(acc, Zb + Tile::point(lane, 0) * J, HS, WSB + Tile::wofs(lane, c), NC * Tile::WROW, W);
+                else       product_loop<J, false>(acc, Zb + Tile::point(lane, 0) * J, HS, wp + Tile::wofs(lane, c), NC * Tile::WROW, W);
+                // (requesting the stash rows of the VJP one neuron ahead, the first ones before the product loop, was
+                //  measured: reverse-U at C2 0.697 ms against 0.662 -- the 8 extra live registers cost more than the latency)
                 if (fused) {
 #pragma unroll
                     for (int n = 0; n < NPT; ++n) {
@@ -1046,9 +1074,11 @@ int launch_bwd_impl(const BwdArgs& a, int grid, cudaStream_t stream) {
     constexpr int J = 1 + NX + NT;
     const int nw = bwd_block_warps(a.net.W, a.net.L, a.net.din, J);
     const size_t smem = bwd_smem_bytes(a.net.W, a.net.L, a.net.din, J);
+    BwdArgs b = a;
+    b.aux = bwd_stage_weights(a.net.W, a.net.L, a.net.din, J) ? 1 : 0;
     // (the dynamic shared-memory attribute was set by bwd_grid -> grid_for for this shape)
-    if (nw <= a.net.NC) mlp_jet_bwd_kernel<ACT, NX, NT, true><<<grid, nw * 32, smem, stream>>>(a);
-    else                mlp_jet_bwd_kernel<ACT, NX, NT, false><<<grid, nw * 32, smem, stream>>>(a);
+    if (nw <= a.net.NC) mlp_jet_bwd_kernel<ACT, NX, NT, true><<<grid, nw * 32, smem, stream>>>(b);
+    else                mlp_jet_bwd_kernel<ACT, NX, NT, false><<<grid, nw * 32, smem, stream>>>(b);
     PDR_CUDA_CHECK(cudaGetLastError());
     return PDEREAD_OK;
 }

@@ -21,15 +21,6 @@ namespace pdr {
 constexpr int PG = 8;                 // neurons per warp
 constexpr int PLAIN_MAX_WARPS = 16;   // widths up to 128
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
-                 :
-                 : "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
 template <int PP>
 __device__ __forceinline__ void vec_load(const float* p, float* v) {
     if constexpr (PP == 4) {
