@@ -20,6 +20,13 @@
  *   - every function returns 0 on success or a negative pderead_status; no exceptions cross.
  *   - workspace: query the *_workspace_bytes function, hand in a device buffer at least that
  *     large (16-byte aligned).  A larger buffer lets the library process more points per chunk.
+ *   - network shapes: any width (the reference takes any Neurons_Per_Layer, Network.py:110-130),
+ *     1..PDEREAD_MAX_HIDDEN_LAYERS hidden layers, input dimension <= PDEREAD_MAX_INPUT_DIM.  The
+ *     kernels keep a tile's activations (2 x width x (32 J + 4) floats, J = 1 + n + m) in shared
+ *     memory; when that exceeds the 227 KB of an SM (width > 148 at J = 6, > 127 at J = 7, > 214 at
+ *     J = 4) the two buffers move to the workspace (one CTA per SM, L2-resident) -- same results,
+ *     lower throughput.  PDEREAD_ERR_UNSUPPORTED_NET is left for shapes whose per-CTA parameter
+ *     accumulators alone exceed shared memory (hidden layers x width beyond ~50 000).
  */
 #ifndef PDEREAD_B200_H
 #define PDEREAD_B200_H

@@ -101,6 +101,16 @@ size_t fwd_smem_bytes_tile(int W, int din, int J, int nwarps, int TP) {
     return sizeof(float) * ((size_t)2 * W * HS + (size_t)din * TP + (size_t)nwarps * J * TP);
 }
 size_t fwd_smem_bytes(int W, int din, int J, int nwarps) { return fwd_smem_bytes_tile(W, din, J, nwarps, tile_points(J)); }
+static const size_t SMEM_MAX = 227 * 1024;    // opt-in dynamic shared memory per CTA on sm_100
+size_t fwd_hbuf_floats(int W, int J) {
+    const int JP = (use_pair_map(J) && J > 1) ? ((J + 1) & ~1) : J;
+    return (size_t)2 * W * (JP * tile_points(J) + 4);
+}
+size_t bwd_hbuf_floats(int W, int J) { return (size_t)2 * W * h_stride(J); }
+size_t fwd_smem_small(int W, int din, int J, int nwarps) {
+    return fwd_smem_bytes(W, din, J, nwarps) - sizeof(float) * fwd_hbuf_floats(W, J);
+}
+bool fwd_spills(int W, int din, int J) { return fwd_smem_bytes(W, din, J, block_warps(W)) > SMEM_MAX; }
 static size_t bwd_smem_bytes_base(int W, int L, int din, int J) {
     const int TP = tile_points(J), HS = h_stride(J);
     const size_t ns = (((size_t)L * W + 1 + (size_t)W * din + W + 7 * L + 3) & ~(size_t)3) + HS;   // + the ones row
@@ -126,6 +136,10 @@ bool bwd_stage_weights(int W, int L, int din, int J) {
 }
 size_t bwd_smem_bytes(int W, int L, int din, int J) {
     return bwd_smem_bytes_base(W, L, din, J) + (bwd_stage_weights(W, L, din, J) ? bwd_wstage_bytes(W, J) + 16 : 0);
+}
+bool bwd_spills(int W, int L, int din, int J) { return bwd_smem_bytes(W, L, din, J) > SMEM_MAX; }
+size_t bwd_smem_small(int W, int L, int din, int J) {
+    return bwd_smem_bytes_base(W, L, din, J) - sizeof(float) * bwd_hbuf_floats(W, J);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -856,7 +870,9 @@ static int check_smem(int W, int L, int din, int J, bool bwd) {
     int dev = 0, maxsm = 0;
     PDR_CUDA_CHECK(cudaGetDevice(&dev));
     PDR_CUDA_CHECK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const size_t need = bwd ? bwd_smem_bytes(W, L, din, J) : fwd_smem_bytes(W, din, J, block_warps(W));
+    size_t need = bwd ? bwd_smem_bytes(W, L, din, J) : fwd_smem_bytes(W, din, J, block_warps(W));
+    if (need > (size_t)maxsm)     // activation buffers go to the workspace; the rest must still fit
+        need = bwd ? bwd_smem_small(W, L, din, J) : fwd_smem_small(W, din, J, block_warps(W));
     return need <= (size_t)maxsm ? PDEREAD_OK : PDEREAD_ERR_UNSUPPORTED_NET;
 }
 
@@ -867,6 +883,7 @@ static int max_grid(const NetDev& n, int J) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     }
+    if (bwd_spills(n.W, n.L, n.din, J)) return sms;
     const size_t smem = bwd_smem_bytes(n.W, n.L, n.din, J) + 1024;
     int occ = (int)((size_t)maxsm / smem);
     const int by_threads = 2048 / (block_warps(n.W) * 32);
@@ -877,6 +894,19 @@ static int max_grid(const NetDev& n, int J) {
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+// workspace floats of the spilled activation buffers of one network (forward and, with need_backward, reverse kernel)
+static size_t spill_floats_bound(const NetDev& n, int J, bool need_backward) {
+    size_t f = 0;
+    if (fwd_spills(n.W, n.din, J)) f += (size_t)sm_count() * fwd_hbuf_floats(n.W, J) + 64;
+    if (need_backward && bwd_spills(n.W, n.L, n.din, J)) f += (size_t)sm_count() * bwd_hbuf_floats(n.W, J) + 64;
+    return f;
+}
 
 // carve helper
 struct Carver {
@@ -998,6 +1028,7 @@ struct FwdPlan {
     TcGeom geom;
     float* wt;    // CUDA-core path: packed transposed weights
     float* img;   // tensor-core path: weight images
+    float* hbuf;  // CUDA-core jet kernel: spilled activation buffers (networks too wide for shared memory), else null
 };
 
 static int plan_forward(const NetDev& n, int J, bool allow_tc, Carver& cv, FwdPlan* p) {
@@ -1011,6 +1042,7 @@ static int plan_forward(const NetDev& n, int J, bool allow_tc, Carver& cv, FwdPl
     } else {
         p->plain = (J == 1) && plain_fits(n, false);
         p->wt = cv.take<float>(packed_floats(n));
+        if (!p->plain && fwd_spills(n.W, n.din, J)) p->hbuf = cv.take<float>((size_t)sm_count() * fwd_hbuf_floats(n.W, J));
     }
     return cv.ok ? PDEREAD_OK : PDEREAD_ERR_WORKSPACE_TOO_SMALL;
 }
@@ -1031,6 +1063,7 @@ static int plan_launch(int act, int nx, int nt, const FwdPlan& p, FwdArgs f, cud
     if (!p.tc) {
         const int TP = tile_points(jet_len(nx, nt));
         f.wt_packed = p.wt;
+        f.hbuf = p.hbuf;
         f.num_tiles = (f.M + TP - 1) / TP;
         return dispatch_fwd(act, nx, nt, f, s);
     }
@@ -1115,6 +1148,7 @@ size_t pderead_sol_derivatives_workspace_bytes(const pderead_net* sol, int m, in
     if (to_netdev(sol, &U) != PDEREAD_OK || M < 0) return 0;
     const int J = jet_len(n, m);
     size_t bytes = align_up(packed_floats(U) * 4, 256) * (need_backward ? 2 : 1);
+    bytes += align_up(spill_floats_bound(U, J, need_backward != 0) * 4, 256) + 512;
     bytes += align_up(tc_image_bytes_bound(U), 256);
     if (need_backward) {
         const GradLayout lay = make_layout(U);
@@ -1161,6 +1195,7 @@ struct BwdPlan {
     bool plain;     // J = 1: register-tiled reverse kernel (tile of 128 points)
     FwdPlan fwd;
     float* wn;      // native packed weights
+    float* hbuf;    // spilled Zb / Yb of the reverse kernel (networks too wide for shared memory), else null
     int grid;       // CTAs of the reverse kernel = number of partial-gradient vectors
     float* gpart;
     size_t stash_pp;   // stash floats per point
@@ -1183,6 +1218,8 @@ static int plan_backward(const NetDev& n, int act, int nx, int nt, bool want_gin
         if (!p->fwd.plain && (rc = check_smem(n.W, n.L, n.din, J, false))) return rc;
         p->fwd.wt = cv.take<float>(packed_floats(n));
         p->wn = cv.take<float>(packed_floats(n));
+        if (!p->fwd.plain && fwd_spills(n.W, n.din, J)) p->fwd.hbuf = cv.take<float>((size_t)sm_count() * fwd_hbuf_floats(n.W, J));
+        if (!p->plain && bwd_spills(n.W, n.L, n.din, J)) p->hbuf = cv.take<float>((size_t)sm_count() * bwd_hbuf_floats(n.W, J));
         if (p->plain) {
             if ((rc = dispatch_plain_bwd_grid(act, n.W, n.L, n.din, (M + 127) / 128, &p->grid))) return rc;
         } else {
@@ -1210,6 +1247,7 @@ static int plan_backward_launch(int act, int nx, int nt, BwdPlan& p, BwdArgs b, 
     b.gpart = p.gpart;
     const int TP = p.plain ? 128 : tile_points(jet_len(nx, nt));
     b.wn_packed = p.wn;
+    b.hbuf = p.plain ? nullptr : p.hbuf;
     b.num_tiles = (b.M + TP - 1) / TP;
     {
         // weight-gradient tiling: a warp owns 10 x (16 TK) outputs, TK in {2, 3, 4}; take the one with the fewest
@@ -1313,6 +1351,7 @@ size_t pderead_mlp_workspace_bytes(const pderead_net* net, int64_t M, int need_b
     NetDev N;
     if (to_netdev(net, &N) != PDEREAD_OK || M < 0) return 0;
     size_t bytes = align_up(packed_floats(N) * 4, 256) * (need_backward ? 2 : 1);
+    bytes += align_up(spill_floats_bound(N, 1, need_backward != 0) * 4, 256) + 512;
     bytes += align_up(tc_image_bytes_bound(N), 256);
     if (need_backward) {
         const GradLayout lay = make_layout(N);
@@ -1370,6 +1409,8 @@ size_t pderead_residual_workspace_bytes(const pderead_net* sol, const pderead_ne
     size_t bytes = 0;
     bytes += align_up(packed_floats(U) * 4, 256) * (need_backward ? 2 : 1);
     bytes += align_up(packed_floats(N) * 4, 256) * (need_backward ? 2 : 1);
+    bytes += align_up(spill_floats_bound(U, jet_len(n, m), need_backward != 0) * 4, 256) + 512;
+    bytes += align_up(spill_floats_bound(N, 1, need_backward != 0) * 4, 256) + 512;
     bytes += align_up(tc_image_bytes_bound(U), 256) + align_up(tc_image_bytes_bound(N), 256);
     bytes += align_up((size_t)chunk * (n + 1) * 4, 256) + align_up((size_t)chunk * 4, 256);   // dxn, dtm
     if (need_backward) {
@@ -1530,6 +1571,7 @@ size_t pderead_extraction_gram_workspace_bytes(const pderead_net* sol, const pde
     if (to_netdev(sol, &U) != PDEREAD_OK || to_netdev(pde, &N) != PDEREAD_OK || M < 0) return 0;
     const long long chunk = round_up_ll(M < 8 * CHUNK_TARGET ? (M > 0 ? M : 1) : 8 * CHUNK_TARGET, CHUNK_ALIGN);
     size_t bytes = align_up(packed_floats(U) * 4, 256) + align_up(packed_floats(N) * 4, 256);
+    bytes += align_up(spill_floats_bound(U, jet_len(n, 0), false) * 4, 256) + align_up(spill_floats_bound(N, 1, false) * 4, 256) + 1024;
     bytes += align_up(tc_image_bytes_bound(U), 256) + align_up(tc_image_bytes_bound(N), 256);
     bytes += align_up((size_t)chunk * (n + 1) * 4, 256) + align_up((size_t)chunk * 4, 256);
     return bytes + 8192;

@@ -89,6 +89,8 @@ struct FwdArgs {
     double* sumsq;
     int aux;                  // mlp_plain_fwd_kernel: number of weight buffers in shared memory
     int aux2;                 // mlp_plain_fwd_kernel with a stash: points per lane of the stash tile (2: 64 points, 4: 128)
+    float* hbuf;              // mlp_jet_fwd_kernel: activation buffers in the workspace ([grid][2][W][HS]) for networks whose
+                              // tile does not fit the shared memory of an SM; null = shared memory
 };
 
 struct BwdArgs {
@@ -107,6 +109,7 @@ struct BwdArgs {
     int wg_mode;
     int accumulate;           // 0: this launch zeroes its partial-gradient vectors first
     int aux;                  // mlp_plain_bwd_kernel: number of weight buffers in shared memory
+    float* hbuf;              // mlp_jet_bwd_kernel: Zb / Yb in the workspace ([grid][2][W][HS]) when they do not fit shared memory
 };
 
 // ---- tensor-core path (tc_jet_kernels.cuh) ----------------------------------------------------
@@ -180,6 +183,14 @@ inline int h_stride(int J) { return J * tile_points(J) + 4; }
 size_t fwd_smem_bytes(int W, int din, int J, int nwarps);
 size_t fwd_smem_bytes_tile(int W, int din, int J, int nwarps, int TP);   // for an explicit tile of TP points
 size_t bwd_smem_bytes(int W, int L, int din, int J);
+// Width ceiling: when the two W x HS activation buffers of a tile exceed the shared memory of an SM the kernels keep
+// them in the workspace instead (one CTA per SM, L2-resident); these say when, and how much shared memory is left
+bool fwd_spills(int W, int din, int J);
+bool bwd_spills(int W, int L, int din, int J);
+size_t fwd_hbuf_floats(int W, int J);     // per CTA
+size_t bwd_hbuf_floats(int W, int J);
+size_t fwd_smem_small(int W, int din, int J, int nwarps);
+size_t bwd_smem_small(int W, int L, int din, int J);
 bool bwd_stage_weights(int W, int L, int din, int J);   // reverse kernel: stage the layer's weights in shared memory
 int block_warps(int W);
 int bwd_block_warps(int W, int L, int din, int J);

@@ -342,9 +342,11 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
     const int W = net.W, L = net.L, din = net.din, NC = net.NC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
-    float* Hbuf0 = smem;
+    // activation buffers: shared memory, or this CTA's slice of the workspace when the network is too wide for it
+    // (block barriers order the CTA's own global-memory accesses just as they order shared memory)
+    float* Hbuf0 = a.hbuf ? a.hbuf + (size_t)blockIdx.x * 2 * W * HS : smem;
     float* Hbuf1 = Hbuf0 + (size_t)W * HS;
-    float* IN = Hbuf1 + (size_t)W * HS;
+    float* IN = a.hbuf ? smem : Hbuf1 + (size_t)W * HS;
     float* RED = IN + din * TP;   // [nwarps][J][TP]
 
     double lsum = 0.0;
@@ -638,9 +640,10 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
     const int W = net.W, L = net.L, din = net.din, NC = net.NC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
-    float* Zb = smem;                          // zbar of the layer above the current weight matrix ...
+    // (a.hbuf: the two buffers live in this CTA's slice of the workspace -- networks too wide for shared memory)
+    float* Zb = a.hbuf ? a.hbuf + (size_t)blockIdx.x * 2 * W * HS : smem;   // zbar of the layer above the current weight matrix ...
     float* Yb = Zb + (size_t)W * HS;           // ... activations of the layer below it (the two swap every layer)
-    float* IN = Yb + (size_t)W * HS;           // [din][TP]
+    float* IN = a.hbuf ? smem : Yb + (size_t)W * HS;   // [din][TP]
     float* SD = IN + din * TP;                 // [J][TP] seeds = d(loss)/d(u_j), factorials folded in
     float* GIN = SD + J * TP;                  // [din][TP]
     float* SACC = GIN + din * TP;              // small-parameter gradient accumulators (persist over tiles)
@@ -994,7 +997,9 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
 // =============================================================================================
 // Resident CTAs for (kernel, block, shared memory) on the current device: attribute + occupancy queries cost
 // several microseconds each, a step launches four such kernels, so the answer is remembered.
-inline int grid_for(const void* kernel, int threads, size_t smem, long long num_tiles, int* grid_out) {
+// one_per_sm: the activation buffers are spilled to the workspace, which is sized for one CTA per SM.
+inline int grid_for(const void* kernel, int threads, size_t smem, long long num_tiles, int* grid_out,
+                    bool one_per_sm = false) {
     struct Entry { const void* k; int threads; size_t smem; int dev; long long resident; };
     constexpr int NCACHE = 32;
     // process-wide, like the attribute: autograd runs the reverse calls on its own thread
@@ -1022,6 +1027,11 @@ inline int grid_for(const void* kernel, int threads, size_t smem, long long num_
         cache[slot] = Entry{kernel, threads, smem, dev, resident};
     }
     long long g = resident;
+    if (one_per_sm) {
+        int sms = 0;
+        PDR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (g > sms) g = sms;
+    }
     if (g > num_tiles) g = num_tiles;
     if (g < 1) g = 1;
     *grid_out = (int)g;
@@ -1032,11 +1042,12 @@ template <int ACT, int NX, int NT, bool STASH, int PPL>
 int launch_fwd_tile(FwdArgs a, cudaStream_t stream) {
     constexpr int J = 1 + NX + NT;
     const int nw = block_warps(a.net.W);
-    const size_t smem = fwd_smem_bytes_tile(a.net.W, a.net.din, J, nw, 32 * PPL);
+    // (a.hbuf is only ever set for the default tile, PPL = PointsPerLane<J>)
+    const size_t smem = a.hbuf ? fwd_smem_small(a.net.W, a.net.din, J, nw) : fwd_smem_bytes_tile(a.net.W, a.net.din, J, nw, 32 * PPL);
     a.num_tiles = (a.M + 32 * PPL - 1) / (32 * PPL);
     const void* k = (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL>;
     int grid = 0;
-    int rc = grid_for(k, nw * 32, smem, a.num_tiles, &grid);
+    int rc = grid_for(k, nw * 32, smem, a.num_tiles, &grid, a.hbuf != nullptr);
     if (rc != PDEREAD_OK) return rc;
     mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL><<<grid, nw * 32, smem, stream>>>(a);
     PDR_CUDA_CHECK(cudaGetLastError());
@@ -1062,20 +1073,23 @@ template <int ACT, int NX, int NT>
 int bwd_grid(int W, int L, int din, long long num_tiles, int* grid_out) {
     constexpr int J = 1 + NX + NT;
     const int nw = bwd_block_warps(W, L, din, J);
-    const size_t smem = bwd_smem_bytes(W, L, din, J);
+    const bool spill = bwd_spills(W, L, din, J);
+    const size_t smem = spill ? bwd_smem_small(W, L, din, J) : bwd_smem_bytes(W, L, din, J);
     const int NC = (W + TN - 1) / TN;
     const void* k = (nw <= NC) ? (const void*)mlp_jet_bwd_kernel<ACT, NX, NT, true>
                                : (const void*)mlp_jet_bwd_kernel<ACT, NX, NT, false>;
-    return grid_for(k, nw * 32, smem, num_tiles, grid_out);
+    return grid_for(k, nw * 32, smem, num_tiles, grid_out, spill);
 }
 
 template <int ACT, int NX, int NT>
 int launch_bwd_impl(const BwdArgs& a, int grid, cudaStream_t stream) {
     constexpr int J = 1 + NX + NT;
     const int nw = bwd_block_warps(a.net.W, a.net.L, a.net.din, J);
-    const size_t smem = bwd_smem_bytes(a.net.W, a.net.L, a.net.din, J);
+    const bool spill = bwd_spills(a.net.W, a.net.L, a.net.din, J);
+    if (spill != (a.hbuf != nullptr)) return PDEREAD_ERR_BAD_ARGUMENT;
+    const size_t smem = spill ? bwd_smem_small(a.net.W, a.net.L, a.net.din, J) : bwd_smem_bytes(a.net.W, a.net.L, a.net.din, J);
     BwdArgs b = a;
-    b.aux = bwd_stage_weights(a.net.W, a.net.L, a.net.din, J) ? 1 : 0;
+    b.aux = (!spill && bwd_stage_weights(a.net.W, a.net.L, a.net.din, J)) ? 1 : 0;
     // (the dynamic shared-memory attribute was set by bwd_grid -> grid_for for this shape)
     if (nw <= a.net.NC) mlp_jet_bwd_kernel<ACT, NX, NT, true><<<grid, nw * 32, smem, stream>>>(b);
     else                mlp_jet_bwd_kernel<ACT, NX, NT, false><<<grid, nw * 32, smem, stream>>>(b);

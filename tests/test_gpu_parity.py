@@ -501,6 +501,10 @@ def test_one_kernel_alternating_between_network_shapes():
     ("Tanh", 3, 65, 2, 96, 1, 3),        # third column block; 7 chunks
     ("Rational", 2, 128, 2, 40, 1, 4),   # J = 6 at width 128: wide blocks (VJP outside the product epilogue)
     ("Tanh", 2, 160, 2, 10, 1, 3),       # J = 5 at width 160: wide blocks with as many chunks as warps
+    ("Rational", 2, 128, 2, 24, 2, 4),   # J = 7 at width 128: the tile's buffers exceed shared memory -> workspace buffers
+    ("Tanh", 2, 200, 2, 300, 1, 2),      # J = 4 at width 200 (pair tile, chunks looped over 16 warps); PDE net of width
+                                         # 300: beyond the register-tiled plain kernels, J = 1 jet kernels
+    ("Sin", 2, 420, 1, 8, 1, 1),         # J = 3 at width 420: forward and reverse buffers both in the workspace
 ])
 def test_gradients_over_odd_shapes(act, LU, WU, LN, WN, m, n):
     """Loss and every parameter gradient against the float64 oracle for shapes that exercise the edges of the
