@@ -328,7 +328,10 @@ __device__ __forceinline__ void input_layer_jet(const NetDev& net, const float* 
 // (Measured and dropped: a single activation buffer updated in place -- outputs wait in their accumulator registers
 // for a barrier, then replace the layer below.  It halves the shared memory, but costs a barrier per layer and, where
 // it buys a second CTA (width 100, J = 6), a 96-register cap: C4 forward 8.59 ms against 8.28, C3 4.18 against 3.72.)
-template <int ACT, int NX, int NT, bool STASH, int PPL>
+// SPILL: the two activation buffers live in this CTA's slice of the workspace (a.hbuf) instead of shared memory --
+// networks too wide for an SM's shared memory.  A separate instantiation, so that the common case keeps its
+// shared-memory address space (LDS / STS instead of generic loads: reverse-U at C2 0.66 ms against 0.94).
+template <int ACT, int NX, int NT, bool STASH, int PPL, bool SPILL>
 __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_kernel(const FwdArgs a) {
     constexpr int J = 1 + NX + NT;
     using Tile = ProdTile<UsePairMap<J>::v, PPL, J>;
@@ -344,9 +347,9 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
 
     // activation buffers: shared memory, or this CTA's slice of the workspace when the network is too wide for it
     // (block barriers order the CTA's own global-memory accesses just as they order shared memory)
-    float* Hbuf0 = a.hbuf ? a.hbuf + (size_t)blockIdx.x * 2 * W * HS : smem;
+    float* Hbuf0 = SPILL ? a.hbuf + (size_t)blockIdx.x * 2 * W * HS : smem;
     float* Hbuf1 = Hbuf0 + (size_t)W * HS;
-    float* IN = a.hbuf ? smem : Hbuf1 + (size_t)W * HS;
+    float* IN = SPILL ? smem : smem + (size_t)2 * W * HS;
     float* RED = IN + din * TP;   // [nwarps][J][TP]
 
     double lsum = 0.0;
@@ -626,7 +629,7 @@ __device__ __forceinline__ void act_vjp_row(const float* z, const float* y, cons
 
 // FUSED: one warp per neuron chunk (blockDim = 32 NC), the VJP runs in the product epilogue.  !FUSED ("wide"
 // blocks of BWD_WIDE_WARPS > NC warps, one CTA per SM): the VJP runs in phase (d), where all warps take part.
-template <int ACT, int NX, int NT, bool FUSED>
+template <int ACT, int NX, int NT, bool FUSED, bool SPILL>
 __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_kernel(const BwdArgs a) {
     constexpr int J = 1 + NX + NT;
     constexpr int PPL = PointsPerLane<J>::v;
@@ -641,9 +644,9 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
     // (a.hbuf: the two buffers live in this CTA's slice of the workspace -- networks too wide for shared memory)
-    float* Zb = a.hbuf ? a.hbuf + (size_t)blockIdx.x * 2 * W * HS : smem;   // zbar of the layer above the current weight matrix ...
+    float* Zb = SPILL ? a.hbuf + (size_t)blockIdx.x * 2 * W * HS : smem;   // zbar of the layer above the current weight matrix ...
     float* Yb = Zb + (size_t)W * HS;           // ... activations of the layer below it (the two swap every layer)
-    float* IN = a.hbuf ? smem : Yb + (size_t)W * HS;   // [din][TP]
+    float* IN = SPILL ? smem : smem + (size_t)2 * W * HS;   // [din][TP]
     float* SD = IN + din * TP;                 // [J][TP] seeds = d(loss)/d(u_j), factorials folded in
     float* GIN = SD + J * TP;                  // [din][TP]
     float* SACC = GIN + din * TP;              // small-parameter gradient accumulators (persist over tiles)
@@ -799,6 +802,8 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                 Tile acc;
                 acc.zero();
                 if (stage) product_loop<J, true>(acc, Zb + Tile::point(lane, 0) * J, HS, WSB + Tile::wofs(lane, c), NC * Tile::WROW, W);
+                // (weight rows requested two k-steps ahead in registers -- the reverse kernel's weights come from L2 --
+                //  were measured: 0.697 ms against 0.663 at C2)
                 else       product_loop<J, false>(acc, Zb + Tile::point(lane, 0) * J, HS, wp + Tile::wofs(lane, c), NC * Tile::WROW, W);
                 // (requesting the stash rows of the VJP one neuron ahead, the first ones before the product loop, was
                 //  measured: reverse-U at C2 0.697 ms against 0.662 -- the 8 extra live registers cost more than the latency)
@@ -1045,11 +1050,13 @@ int launch_fwd_tile(FwdArgs a, cudaStream_t stream) {
     // (a.hbuf is only ever set for the default tile, PPL = PointsPerLane<J>)
     const size_t smem = a.hbuf ? fwd_smem_small(a.net.W, a.net.din, J, nw) : fwd_smem_bytes_tile(a.net.W, a.net.din, J, nw, 32 * PPL);
     a.num_tiles = (a.M + 32 * PPL - 1) / (32 * PPL);
-    const void* k = (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL>;
+    const void* k = a.hbuf ? (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, true>
+                           : (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, false>;
     int grid = 0;
     int rc = grid_for(k, nw * 32, smem, a.num_tiles, &grid, a.hbuf != nullptr);
     if (rc != PDEREAD_OK) return rc;
-    mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL><<<grid, nw * 32, smem, stream>>>(a);
+    if (a.hbuf) mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, true><<<grid, nw * 32, smem, stream>>>(a);
+    else        mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, false><<<grid, nw * 32, smem, stream>>>(a);
     PDR_CUDA_CHECK(cudaGetLastError());
     return PDEREAD_OK;
 }
@@ -1076,8 +1083,10 @@ int bwd_grid(int W, int L, int din, long long num_tiles, int* grid_out) {
     const bool spill = bwd_spills(W, L, din, J);
     const size_t smem = spill ? bwd_smem_small(W, L, din, J) : bwd_smem_bytes(W, L, din, J);
     const int NC = (W + TN - 1) / TN;
-    const void* k = (nw <= NC) ? (const void*)mlp_jet_bwd_kernel<ACT, NX, NT, true>
-                               : (const void*)mlp_jet_bwd_kernel<ACT, NX, NT, false>;
+    const void* k = spill ? ((nw <= NC) ? (const void*)mlp_jet_bwd_kernel<ACT, NX, NT, true, true>
+                                        : (const void*)mlp_jet_bwd_kernel<ACT, NX, NT, false, true>)
+                          : ((nw <= NC) ? (const void*)mlp_jet_bwd_kernel<ACT, NX, NT, true, false>
+                                        : (const void*)mlp_jet_bwd_kernel<ACT, NX, NT, false, false>);
     return grid_for(k, nw * 32, smem, num_tiles, grid_out, spill);
 }
 
@@ -1091,8 +1100,13 @@ int launch_bwd_impl(const BwdArgs& a, int grid, cudaStream_t stream) {
     BwdArgs b = a;
     b.aux = (!spill && bwd_stage_weights(a.net.W, a.net.L, a.net.din, J)) ? 1 : 0;
     // (the dynamic shared-memory attribute was set by bwd_grid -> grid_for for this shape)
-    if (nw <= a.net.NC) mlp_jet_bwd_kernel<ACT, NX, NT, true><<<grid, nw * 32, smem, stream>>>(b);
-    else                mlp_jet_bwd_kernel<ACT, NX, NT, false><<<grid, nw * 32, smem, stream>>>(b);
+    if (spill) {
+        if (nw <= a.net.NC) mlp_jet_bwd_kernel<ACT, NX, NT, true, true><<<grid, nw * 32, smem, stream>>>(b);
+        else                mlp_jet_bwd_kernel<ACT, NX, NT, false, true><<<grid, nw * 32, smem, stream>>>(b);
+    } else {
+        if (nw <= a.net.NC) mlp_jet_bwd_kernel<ACT, NX, NT, true, false><<<grid, nw * 32, smem, stream>>>(b);
+        else                mlp_jet_bwd_kernel<ACT, NX, NT, false, false><<<grid, nw * 32, smem, stream>>>(b);
+    }
     PDR_CUDA_CHECK(cudaGetLastError());
     return PDEREAD_OK;
 }
