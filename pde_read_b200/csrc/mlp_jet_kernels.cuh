@@ -46,6 +46,27 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// Weight loads of the layer products: read-only path, and (PDR_W_EVICT_LAST) kept in L1 in preference to everything
+// else that passes through it.
+__device__ __forceinline__ float4 ldg_w4(const float4* p) {
+#if PDR_W_EVICT_LAST
+    float4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ float ldg_w1(const float* p) {
+#if PDR_W_EVICT_LAST
+    float v;
+    asm volatile("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 template <int ACT>
 __device__ __forceinline__ void load_ab(const NetDev& net, int l, float* ab) {
     if (ACT == ACT_RATIONAL) {
@@ -185,8 +206,8 @@ struct ProdTile<true, PPL, J> {
     // wk: this thread's weights of row k
     template <int JP, bool WS>
     __device__ __forceinline__ void step(const float* __restrict__ hk, const float* __restrict__ wk) {
-        const float4 w4 = WS ? *reinterpret_cast<const float4*>(wk) : __ldg(reinterpret_cast<const float4*>(wk));
-        const float w5 = WS ? wk[4] : __ldg(wk + 4);
+        const float4 w4 = WS ? *reinterpret_cast<const float4*>(wk) : ldg_w4(reinterpret_cast<const float4*>(wk));
+        const float w5 = WS ? wk[4] : ldg_w1(wk + 4);
         const float wv[TH] = {w4.x, w4.y, w4.z, w4.w, w5};
         float hv[QP][J];
 #pragma unroll
@@ -235,9 +256,9 @@ struct ProdTile<false, PPL, J> {
     template <int JP, bool WS>
     __device__ __forceinline__ void step(const float* __restrict__ hk, const float* __restrict__ wk) {
         const float4* w4p = reinterpret_cast<const float4*>(wk);
-        const float4 b0 = WS ? w4p[0] : __ldg(w4p);
-        const float4 b1 = WS ? w4p[1] : __ldg(w4p + 1);
-        const float4 b2 = WS ? w4p[2] : __ldg(w4p + 2);
+        const float4 b0 = WS ? w4p[0] : ldg_w4(w4p);
+        const float4 b1 = WS ? w4p[1] : ldg_w4(w4p + 1);
+        const float4 b2 = WS ? w4p[2] : ldg_w4(w4p + 2);
         const float2 bw[TNP_LANE / 2] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
                                          make_float2(b1.z, b1.w), make_float2(b2.x, b2.y), make_float2(b2.z, b2.w)};
 #pragma unroll
@@ -282,6 +303,24 @@ __device__ __forceinline__ void stash_store(float* p, const float* z) {
 #pragma unroll
         for (int j = 0; j < J; ++j) p[j] = z[j];
     }
+}
+// the forward kernel's stash rows go to HBM and are not read again by this kernel: streaming stores
+template <int J>
+__device__ __forceinline__ void stash_store_global(float* p, const float* z) {
+#if PDR_STASH_CS
+    if constexpr (J % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < J; j += 4) __stcs(reinterpret_cast<float4*>(p + j), make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]));
+    } else if constexpr (J % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < J; j += 2) __stcs(reinterpret_cast<float2*>(p + j), make_float2(z[j], z[j + 1]));
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) __stcs(p + j, z[j]);
+    }
+#else
+    stash_store<J>(p, z);
+#endif
 }
 template <int J>
 __device__ __forceinline__ void stash_load(const float* p, float* z) {
@@ -347,9 +386,16 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
 
     // activation buffers: shared memory, or this CTA's slice of the workspace when the network is too wide for it
     // (block barriers order the CTA's own global-memory accesses just as they order shared memory)
-    float* Hbuf0 = SPILL ? a.hbuf + (size_t)blockIdx.x * 2 * W * HS : smem;
+    // (keep these three expressions as they are: ptxas' schedule of the product loop below flips with the way they
+    //  are written -- J = 6 forward 8.3 ms against 10.2 for `smem + 2 W HS`; check C4 after touching this kernel)
+    float* Hbuf0 = smem;
     float* Hbuf1 = Hbuf0 + (size_t)W * HS;
-    float* IN = SPILL ? smem : smem + (size_t)2 * W * HS;
+    float* IN = Hbuf1 + (size_t)W * HS;
+    if constexpr (SPILL) {
+        Hbuf0 = a.hbuf + (size_t)blockIdx.x * 2 * W * HS;
+        Hbuf1 = Hbuf0 + (size_t)W * HS;
+        IN = smem;
+    }
     float* RED = IN + din * TP;   // [nwarps][J][TP]
 
     double lsum = 0.0;
@@ -431,7 +477,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
                             act_fwd<ACT, NX, NT, float>(z, ab, y);
                             if (STASH) {
                                 if (ACT == ACT_TANH) z[0] = y[0];       // see "rows of the reverse pass"
-                                stash_store<J>(a.stash + (((size_t)tile * (L - 1) + (l - 1)) * W + i) * (J * TP) + pt * J, z);
+                                stash_store_global<J>(a.stash + (((size_t)tile * (L - 1) + (l - 1)) * W + i) * (J * TP) + pt * J, z);
                             }
                             if (last) {
 #pragma unroll
@@ -644,9 +690,14 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
     // (a.hbuf: the two buffers live in this CTA's slice of the workspace -- networks too wide for shared memory)
-    float* Zb = SPILL ? a.hbuf + (size_t)blockIdx.x * 2 * W * HS : smem;   // zbar of the layer above the current weight matrix ...
+    float* Zb = smem;                          // zbar of the layer above the current weight matrix ...
     float* Yb = Zb + (size_t)W * HS;           // ... activations of the layer below it (the two swap every layer)
-    float* IN = SPILL ? smem : smem + (size_t)2 * W * HS;   // [din][TP]
+    float* IN = Yb + (size_t)W * HS;           // [din][TP]
+    if constexpr (SPILL) {
+        Zb = a.hbuf + (size_t)blockIdx.x * 2 * W * HS;
+        Yb = Zb + (size_t)W * HS;
+        IN = smem;
+    }
     float* SD = IN + din * TP;                 // [J][TP] seeds = d(loss)/d(u_j), factorials folded in
     float* GIN = SD + J * TP;                  // [din][TP]
     float* SACC = GIN + din * TP;              // small-parameter gradient accumulators (persist over tiles)
