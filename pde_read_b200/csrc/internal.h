@@ -25,6 +25,9 @@ constexpr int TNP = TNP_PAIR;       // workspace sizing: the larger of the two
 #ifndef PDR_STASH_CS
 #define PDR_STASH_CS 0              // forward kernel: streaming stores for the stash
 #endif
+#ifndef PDR_PROD_UNROLL
+#define PDR_PROD_UNROLL 2           // unroll factor of the layer-product loop
+#endif
 #ifndef PDR_PAIR_MAXJ
 #define PDR_PAIR_MAXJ 4             // longest jet that uses the pair tile (A/B builds: PDR_EXTRA_CFLAGS=-DPDR_PAIR_MAXJ=..)
 #endif

@@ -280,7 +280,8 @@ struct ProdTile<false, PPL, J> {
 template <int JP, bool WS, class Tile>
 __device__ __forceinline__ void product_loop(Tile& acc, const float* __restrict__ h, int HS,
                                              const float* __restrict__ w, int wstride, int W) {
-#pragma unroll 2
+    constexpr int UNROLL = PDR_PROD_UNROLL;
+#pragma unroll UNROLL
     for (int k = 0; k < W; ++k) {
         acc.template step<JP, WS>(h, w);
         w += wstride;

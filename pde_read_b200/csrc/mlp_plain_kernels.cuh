@@ -20,6 +20,18 @@ namespace pdr {
 
 constexpr int PG = 8;                 // neurons per warp
 constexpr int PLAIN_MAX_WARPS = 16;   // widths up to 128
+// Narrow networks (<= 7 warps, widths up to 56) get their own instantiation with a register cap that lets a third CTA
+// share the SM (width 50: 7 warps, 70 KB of shared memory per CTA; at ptxas' free choice of 99 / 128 registers only two
+// CTAs were resident and `barrier` was the top stall of the reverse kernel).
+constexpr int PLAIN_NARROW_WARPS = 7;
+#ifndef PDR_PLAIN_NARROW_CTAS
+#define PDR_PLAIN_NARROW_CTAS 3
+#endif
+template <bool NARROW>
+struct PlainBounds {
+    static constexpr int threads = (NARROW ? PLAIN_NARROW_WARPS : PLAIN_MAX_WARPS) * 32;
+    static constexpr int ctas = NARROW ? PDR_PLAIN_NARROW_CTAS : 1;
+};
 
 template <int PP>
 __device__ __forceinline__ void vec_load(const float* p, float* v) {
@@ -48,8 +60,8 @@ __device__ __forceinline__ void vec_store(float* p, const float* v) {
 
 // a.wt_packed: [L-1][W][WP] with wt[l][k][i] = W_{l+1}[i][k] (zero for i >= W), WP = 8 * ceil(W / 8)
 // a.aux: number of weight buffers in shared memory (1 or 2)
-template <int ACT, bool STASH, int PP>
-__global__ void __launch_bounds__(PLAIN_MAX_WARPS * 32) mlp_plain_fwd_kernel(const FwdArgs a) {
+template <int ACT, bool STASH, int PP, bool NARROW>
+__global__ void __launch_bounds__(PlainBounds<NARROW>::threads, PlainBounds<NARROW>::ctas) mlp_plain_fwd_kernel(const FwdArgs a) {
     constexpr int TP = 32 * PP;
     constexpr int HS = TP + 4;
 
@@ -252,11 +264,13 @@ int launch_plain_tile(FwdArgs a, cudaStream_t stream) {
     a.aux = (c2 >= 1 && (c2 == c1 || c2 >= 3)) ? 2 : 1;
     const size_t smem = a.aux == 2 ? s2 : s1;
     a.num_tiles = (a.M + 32 * PP - 1) / (32 * PP);
-    const void* k = (const void*)mlp_plain_fwd_kernel<ACT, STASH, PP>;
+    const bool narrow = nw <= PLAIN_NARROW_WARPS;
+    const void* k = narrow ? (const void*)mlp_plain_fwd_kernel<ACT, STASH, PP, true> : (const void*)mlp_plain_fwd_kernel<ACT, STASH, PP, false>;
     int grid = 0;
     int rc = grid_for(k, nw * 32, smem, a.num_tiles, &grid);
     if (rc != PDEREAD_OK) return rc;
-    mlp_plain_fwd_kernel<ACT, STASH, PP><<<grid, nw * 32, smem, stream>>>(a);
+    if (narrow) mlp_plain_fwd_kernel<ACT, STASH, PP, true><<<grid, nw * 32, smem, stream>>>(a);
+    else        mlp_plain_fwd_kernel<ACT, STASH, PP, false><<<grid, nw * 32, smem, stream>>>(a);
     PDR_CUDA_CHECK(cudaGetLastError());
     return PDEREAD_OK;
 }
@@ -279,8 +293,8 @@ int launch_plain_fwd(const FwdArgs& a, cudaStream_t stream) {
 //   (d) Zb <- y of the layer below from the stash, for the next weight gradient.
 // a.wn_packed: [L-1][W][WP] with wn[l][i][k] = W_{l+1}[i][k] (zero for k >= W); a.aux = weight buffers (1 or 2)
 // =====================================================================================================================
-template <int ACT>
-__global__ void __launch_bounds__(PLAIN_MAX_WARPS * 32) mlp_plain_bwd_kernel(const BwdArgs a) {
+template <int ACT, bool NARROW>
+__global__ void __launch_bounds__(PlainBounds<NARROW>::threads, PlainBounds<NARROW>::ctas) mlp_plain_bwd_kernel(const BwdArgs a) {
     constexpr int PP = 4, TP = 32 * PP, HS = TP + 4;
 
     extern __shared__ __align__(16) float smem[];
@@ -586,7 +600,8 @@ template <int ACT>
 int plain_bwd_grid(int W, int L, int din, long long num_tiles, int* grid_out) {
     const int nw = (W + PG - 1) / PG;
     const size_t smem = plain_bwd_smem_bytes(W, L, din, plain_bwd_nbuf(W, L, din));
-    return grid_for((const void*)mlp_plain_bwd_kernel<ACT>, nw * 32, smem, num_tiles, grid_out);
+    const void* k = nw <= PLAIN_NARROW_WARPS ? (const void*)mlp_plain_bwd_kernel<ACT, true> : (const void*)mlp_plain_bwd_kernel<ACT, false>;
+    return grid_for(k, nw * 32, smem, num_tiles, grid_out);
 }
 
 template <int ACT>
@@ -596,7 +611,8 @@ int launch_plain_bwd(const BwdArgs& a0, int grid, cudaStream_t stream) {
     const int nw = (W + PG - 1) / PG;
     a.aux = plain_bwd_nbuf(W, L, din);
     const size_t smem = plain_bwd_smem_bytes(W, L, din, a.aux);
-    mlp_plain_bwd_kernel<ACT><<<grid, nw * 32, smem, stream>>>(a);
+    if (nw <= PLAIN_NARROW_WARPS) mlp_plain_bwd_kernel<ACT, true><<<grid, nw * 32, smem, stream>>>(a);
+    else                          mlp_plain_bwd_kernel<ACT, false><<<grid, nw * 32, smem, stream>>>(a);
     PDR_CUDA_CHECK(cudaGetLastError());
     return PDEREAD_OK;
 }
