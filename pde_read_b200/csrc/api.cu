@@ -93,6 +93,12 @@ int block_warps(int W) {
 // -- the products use one warp per neuron chunk, the activation phases (latency-bound) use all of them.
 int bwd_block_warps(int W, int L, int din, int J) {
     const int nw = block_warps(W);
+    static int wide = -1;     // PDEREAD_BWD_WIDE=0: never the 16-warp block (A/B measurements)
+    if (wide < 0) {
+        const char* e = getenv("PDEREAD_BWD_WIDE");
+        wide = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (!wide) return nw;
     return (bwd_smem_bytes(W, L, din, J) > 112 * 1024 && nw < BWD_WIDE_WARPS) ? BWD_WIDE_WARPS : nw;
 }
 size_t fwd_smem_bytes_tile(int W, int din, int J, int nwarps, int TP) {
@@ -119,6 +125,20 @@ static size_t bwd_smem_bytes_base(int W, int L, int din, int J) {
 static size_t bwd_wstage_bytes(int W, int J) {
     const int NC = (W + TN - 1) / TN;
     return sizeof(float) * (size_t)W * NC * (use_pair_map(J) ? TNP_PAIR : TNP_LANE);
+}
+// Forward kernel: per-warp weight slices in shared memory where they fit without costing a resident CTA (width 100,
+// J = 6: one CTA per SM either way).
+size_t fwd_wstage_bytes(int W, int L, int J, size_t base_smem) {
+    static int mode = -1;     // PDEREAD_FWD_STAGE=0|1 overrides the rule below (A/B measurements)
+    if (mode < 0) {
+        const char* e = getenv("PDEREAD_FWD_STAGE");
+        mode = !e ? 2 : (e[0] == '1' ? 1 : 0);
+    }
+    const int NC = (W + TN - 1) / TN;
+    if (!mode || L < 2 || NC > MAX_WARPS) return 0;
+    const size_t extra = bwd_wstage_bytes(W, J) + 16, sm = 227 * 1024;
+    if (base_smem + extra > sm) return 0;
+    return (mode == 1 || sm / (base_smem + extra + 1024) == sm / (base_smem + 1024)) ? extra : 0;
 }
 bool bwd_stage_weights(int W, int L, int din, int J) {
     static int mode = -1;     // PDEREAD_BWD_STAGE=0|1 overrides the rule below (A/B measurements)

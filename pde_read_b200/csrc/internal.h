@@ -200,7 +200,9 @@ size_t fwd_hbuf_floats(int W, int J);     // per CTA
 size_t bwd_hbuf_floats(int W, int J);
 size_t fwd_smem_small(int W, int din, int J, int nwarps);
 size_t bwd_smem_small(int W, int L, int din, int J);
-bool bwd_stage_weights(int W, int L, int din, int J);   // reverse kernel: stage the layer's weights in shared memory
+bool bwd_stage_weights(int W, int L, int din, int J);
+// forward kernel: bytes of the per-warp weight slices to add to `base_smem`, or 0 when staging is off for this shape
+size_t fwd_wstage_bytes(int W, int L, int J, size_t base_smem);   // reverse kernel: stage the layer's weights in shared memory
 int block_warps(int W);
 int bwd_block_warps(int W, int L, int din, int J);
 

@@ -371,8 +371,13 @@ __device__ __forceinline__ void input_layer_jet(const NetDev& net, const float* 
 // SPILL: the two activation buffers live in this CTA's slice of the workspace (a.hbuf) instead of shared memory --
 // networks too wide for an SM's shared memory.  A separate instantiation, so that the common case keeps its
 // shared-memory address space (LDS / STS instead of generic loads: reverse-U at C2 0.66 ms against 0.94).
-template <int ACT, int NX, int NT, bool STASH, int PPL, bool SPILL>
+// MODE (forward kernel): 0 = buffers in shared memory, weights through the read-only path; 1 = the same with per-warp
+// weight slices staged in shared memory; 2 = SPILL.  Compile-time, not a run-time flag: ptxas' schedule of the product
+// loop in mode 0 changes (C3 forward 3.71 -> 4.30 ms) as soon as the staging code shares its function.
+constexpr int FWD_PLAIN = 0, FWD_WSTAGE = 1, FWD_SPILL = 2;
+template <int ACT, int NX, int NT, bool STASH, int PPL, int MODE>
 __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_kernel(const FwdArgs a) {
+    constexpr bool SPILL = (MODE == FWD_SPILL);
     constexpr int J = 1 + NX + NT;
     using Tile = ProdTile<UsePairMap<J>::v, PPL, J>;
     constexpr int JP = Tile::JP_FWD;
@@ -402,8 +407,27 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
     double lsum = 0.0;
     const float* wout = net.w[L];
 
+    // MODE 1 (one chunk per warp, room in shared memory): every warp keeps ITS slice of the layer's packed weights
+    // -- the WROW columns of its chunk, all W rows -- in shared memory.  No other warp reads that slice, so the warp
+    // requests the next layer's copy (cp.async) as soon as its own product loop is done and the copy overlaps its
+    // activation epilogue; the barrier that ends the layer also publishes the copy.
+    constexpr bool wstage = (MODE == FWD_WSTAGE);
+    [[maybe_unused]] float* WSL = RED + (size_t)nwarps * J * TP + (size_t)warp * W * Tile::WROW;     // this warp's slice [W][WROW]
+    [[maybe_unused]] auto stage_slice = [&](int l) {
+        const float* src = a.wt_packed + (size_t)(l - 1) * W * NC * Tile::WROW + warp * Tile::WROW;
+        constexpr int V = Tile::WROW / 4;
+        for (int idx = lane; idx < W * V; idx += 32) {
+            const int row = idx / V, part4 = idx - row * V;
+            cp_async16(WSL + row * Tile::WROW + part4 * 4, src + (size_t)row * NC * Tile::WROW + part4 * 4);
+        }
+        cp_async_commit();
+    };
+
     for (long long tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         const long long p0 = tile * TP;
+        if constexpr (wstage) {
+            if (L > 1) stage_slice(1);             // (the slice was last read before the barrier that ended the previous tile)
+        }
         for (int idx = threadIdx.x; idx < din * TP; idx += blockDim.x) {
             const int pt = idx / din, d = idx - pt * din;
             const long long p = p0 + pt;
@@ -445,6 +469,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
                 }
             }
         }
+        if constexpr (wstage) cp_async_wait_all();
         __syncthreads();
 
         // ---- hidden layers 1 .. L-1 ------------------------------------------------------
@@ -463,7 +488,12 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
 #pragma unroll
                     for (int q = 0; q < QP; ++q) acc.set(n, q, 0, bv);
                 }
-                product_loop<JP, false>(acc, Hin + Tile::point(lane, 0) * JP, HS, wp + Tile::wofs(lane, c), NC * Tile::WROW, W);
+                if constexpr (wstage) {
+                    product_loop<JP, true>(acc, Hin + Tile::point(lane, 0) * JP, HS, WSL + Tile::wofs(lane, 0), Tile::WROW, W);
+                    if (!last) stage_slice(l + 1);
+                } else {
+                    product_loop<JP, false>(acc, Hin + Tile::point(lane, 0) * JP, HS, wp + Tile::wofs(lane, c), NC * Tile::WROW, W);
+                }
 #pragma unroll
                 for (int n = 0; n < NPT; ++n) {
                     const int i = Tile::neuron(lane, c, n);
@@ -490,6 +520,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
                     }
                 }
             }
+            if constexpr (wstage) cp_async_wait_all();
             __syncthreads();
             float* t = Hin; Hin = Hout; Hout = t;
         }
@@ -1100,15 +1131,23 @@ int launch_fwd_tile(FwdArgs a, cudaStream_t stream) {
     constexpr int J = 1 + NX + NT;
     const int nw = block_warps(a.net.W);
     // (a.hbuf is only ever set for the default tile, PPL = PointsPerLane<J>)
-    const size_t smem = a.hbuf ? fwd_smem_small(a.net.W, a.net.din, J, nw) : fwd_smem_bytes_tile(a.net.W, a.net.din, J, nw, 32 * PPL);
+    size_t smem = a.hbuf ? fwd_smem_small(a.net.W, a.net.din, J, nw) : fwd_smem_bytes_tile(a.net.W, a.net.din, J, nw, 32 * PPL);
+    a.aux = 0;
+    if (!a.hbuf) {
+        const size_t extra = fwd_wstage_bytes(a.net.W, a.net.L, J, smem);
+        if (extra) { smem += extra; a.aux = 1; }
+    }
     a.num_tiles = (a.M + 32 * PPL - 1) / (32 * PPL);
-    const void* k = a.hbuf ? (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, true>
-                           : (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, false>;
+    const int mode = a.hbuf ? FWD_SPILL : (a.aux ? FWD_WSTAGE : FWD_PLAIN);
+    const void* k = mode == FWD_SPILL    ? (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, FWD_SPILL>
+                    : mode == FWD_WSTAGE ? (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, FWD_WSTAGE>
+                                         : (const void*)mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, FWD_PLAIN>;
     int grid = 0;
     int rc = grid_for(k, nw * 32, smem, a.num_tiles, &grid, a.hbuf != nullptr);
     if (rc != PDEREAD_OK) return rc;
-    if (a.hbuf) mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, true><<<grid, nw * 32, smem, stream>>>(a);
-    else        mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, false><<<grid, nw * 32, smem, stream>>>(a);
+    if (mode == FWD_SPILL)       mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, FWD_SPILL><<<grid, nw * 32, smem, stream>>>(a);
+    else if (mode == FWD_WSTAGE) mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, FWD_WSTAGE><<<grid, nw * 32, smem, stream>>>(a);
+    else                         mlp_jet_fwd_kernel<ACT, NX, NT, STASH, PPL, FWD_PLAIN><<<grid, nw * 32, smem, stream>>>(a);
     PDR_CUDA_CHECK(cudaGetLastError());
     return PDEREAD_OK;
 }
