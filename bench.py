@@ -56,7 +56,7 @@ CONFIGS = {
                ref_chunk=1000, ref_sample=5000, scaling="strong", extraction=True, steps=10),
     "C5S": dict(desc="Extraction stress shape: U 5x100 Rational, N 5x100 Rational, n=4, degree K=5 library (C=252) over 10M points sharded over the GPUs",
                 act="Rational", LU=5, WU=100, LN=5, WN=100, m=1, n=4, K=5, M=10_000_000, box=[[0.0, 5.0], [-5.0, 4.96]],
-                ref_chunk=1000, ref_sample=2000, scaling="strong", extraction=True, steps=3),
+                ref_chunk=1000, ref_sample=1000, ref_steps=2, scaling="strong", extraction=True, steps=3),
 }
 ALSO = ("C3", "C4", "C5", "C5S")
 TAGS = {0: "other", 1: "pack_weights", 2: "jet_fwd<U>", 3: "mlp_fwd<N>", 4: "mlp_bwd<N>", 5: "jet_bwd<U>",
@@ -431,22 +431,34 @@ def run_ours(name, c, env, steps, warmup, with_cpu, peaks):
     C = library_columns(c["n"], c["K"]) if extraction else 0
     d2h = 4 if not extraction else 4 * (C * C + (C + 1) + 3 * C)
 
-    # comm share of the step (multi-GPU): events around one extra all-reduce of the step's payload, for context
-    comm_ms = None
+    # comm share of the step (multi-GPU): events around the step's exchange -- the reducer's in-place sum of a buffer of
+    # the step's payload size (peer-memory all-reduce on one box, NCCL otherwise) -- and around NCCL's for comparison
+    comm_ms, comm_nccl_ms, comm_kind = None, None, None
     if world > 1 and not extraction:
+        from pde_read_b200 import Loss_Functions as LF
+        red = LF.get_reducer() if hasattr(LF, "get_reducer") else None
         nflat = sum((p.numel() + 3) // 4 * 4 for p in params) + 4
         buf = torch.zeros(nflat, dtype=torch.float32, device=dev)
-        for _ in range(3):
-            dist.all_reduce(buf)
-        torch.cuda.synchronize()
-        dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            dist.all_reduce(buf)
-        e1.record()
-        e1.synchronize()
-        comm_ms = e0.elapsed_time(e1) / 10
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            e1.synchronize()
+            return e0.elapsed_time(e1) / 10
+
+        comm_nccl_ms = timed(lambda: dist.all_reduce(buf))
+        if red is not None and hasattr(red, "_sum_flat"):
+            comm_ms = timed(lambda: red._sum_flat(buf))
+            comm_kind = "peer memory (pderead_peer_allreduce)" if getattr(red, "_peer", None) is not None and red._peer.ok else "nccl"
+        else:
+            comm_ms, comm_kind = comm_nccl_ms, "nccl"
 
     if rank != 0:
         return None
@@ -505,7 +517,7 @@ def run_ours(name, c, env, steps, warmup, with_cpu, peaks):
     # ------------------------------------------------ CPU baseline beside it (bounded sample, rank 0, N = 1 only)
     cpu = None
     if with_cpu and world == 1:
-        r = time_cpu_reference(c, sd_u, sd_n, c["ref_sample"], steps=3, warmup=1, budget_s=30.0)
+        r = time_cpu_reference(c, sd_u, sd_n, c["ref_sample"], steps=c.get("ref_steps", 3), warmup=1, budget_s=30.0)
         cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
     line = {
@@ -527,6 +539,8 @@ def run_ours(name, c, env, steps, warmup, with_cpu, peaks):
     }
     if comm_ms is not None:
         line["comm_ms"] = comm_ms
+        line["comm"] = {"exchange": comm_kind, "ms": comm_ms, "nccl_all_reduce_ms": comm_nccl_ms,
+                        "note": "CUDA events around 10 back-to-back exchanges of the step's payload"}
     return line
 
 
@@ -624,7 +638,7 @@ def main():
         F.release_workspaces()
         torch.cuda.empty_cache()
         try:
-            extra[a] = run_ours(a, ca, env, ca["steps"], 3, not args.no_cpu_baseline and a != "C5S", peaks)
+            extra[a] = run_ours(a, ca, env, ca["steps"], 3, not args.no_cpu_baseline, peaks)
         except Exception as e:                      # an "also" workload must never take the headline line down
             extra[a] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if rank == 0:

@@ -234,6 +234,28 @@ int pderead_sgd_step(float* d_params, const float* d_grads, float* d_momentum_bu
 int pderead_loss_tail_pack(const double* d_sum_sq, int64_t M_local, float* d_tail4, void* stream);
 int pderead_loss_tail_unpack(const float* d_tail4, int64_t scale, double* d_out3, void* stream);
 
+/* ---- the per-step exchange over NVLink peer memory (one box, one process per GPU) ----------------------------
+ * Replaces the NCCL all-reduce of the packed float32 buffer [dU | dN | sum(R^2) | count] that ends a sharded
+ * Collocation_Loss step (reference semantics: the mean of Loss_Functions.py:65 and the gradient sums of
+ * Loss.backward(), Test_Train.py:99-100, over ALL points).  Every rank writes its buffer into a slot of every
+ * peer's receive area (remote stores), raises a flag there, then sums the slots of its own area in rank order: one
+ * kernel on the caller's stream, bit-identical results on all ranks, no host synchronisation.
+ *   pderead_peer_alloc      cudaMalloc's this rank's receive area for `world` ranks and buffers of up to cap_floats
+ *                           floats, zeroes it and returns its 64-byte CUDA IPC handle (the one place where the library
+ *                           allocates device memory: the handle must cover exactly one allocation);
+ *   pderead_peer_open       maps a peer's area from its handle (peer access is enabled on demand);
+ *   pderead_peer_allreduce  d_buf[0..n) <- sum over ranks, in place; n % 4 == 0, d_buf 16-byte aligned;
+ *                           d_peer_areas = DEVICE array of `world` area pointers (own area at index rank).  Collective:
+ *                           every rank must call it the same number of times with the same n.
+ */
+size_t pderead_peer_area_bytes(int world, int cap_floats);
+int pderead_peer_alloc(int world, int cap_floats, void** d_area, unsigned char* handle64);
+int pderead_peer_open(const unsigned char* handle64, void** d_area);
+int pderead_peer_close(void* d_area);
+int pderead_peer_free(void* d_area);
+int pderead_peer_allreduce(float* d_buf, int64_t n, void* const* d_peer_areas, void* d_local_area, int rank, int world,
+                           int cap_floats, void* stream);
+
 /* ---- measurement helper ---------------------------------------------------------------------------
  * Runs a register-resident FFMA loop on every SM (`iters` dependent FMA chains per thread) so that
  * bench.py can measure the FP32 FMA peak that bounds this path.  variant 0: scalar FFMA,

@@ -17,6 +17,10 @@ def set_reducer(reducer) -> None:
     _reducer = reducer
 
 
+def get_reducer():
+    return _reducer
+
+
 def Collocation_Loss(
         Sol_NN: Neural_Network,
         PDE_NN: Neural_Network,

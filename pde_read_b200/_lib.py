@@ -98,6 +98,12 @@ PROTOTYPES = {
                                  c_void_p, c_void_p]),
     "pderead_loss_tail_pack": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "pderead_loss_tail_unpack": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "pderead_peer_area_bytes": (c_size_t, [c_int, c_int]),
+    "pderead_peer_alloc": (c_int, [c_int, c_int, c_void_p, c_void_p]),
+    "pderead_peer_open": (c_int, [c_void_p, c_void_p]),
+    "pderead_peer_close": (c_int, [c_void_p]),
+    "pderead_peer_free": (c_int, [c_void_p]),
+    "pderead_peer_allreduce": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pderead_generate_points": (c_int, [POINTER(c_double), c_int, c_int64, c_uint64, c_uint64, c_void_p, c_void_p]),
     "pderead_fma_peak_probe": (c_int, [c_int, c_int, c_void_p, POINTER(c_double), c_void_p]),
     "pderead_debug_stage_events": (c_int, [POINTER(c_void_p), c_int]),

@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -
                 bwd = 1 if (nx, nt) in BWD_COMBOS else 0
                 jobs_list.append([NVCC] + CFLAGS + ["-DPDR_ACT=%d" % act, "-DPDR_NX=%d" % nx, "-DPDR_NT=%d" % nt,
                                                     "-DPDR_BWD=%d" % bwd, "-c", src, "-o", obj])
-    for name in ("api", "extraction"):
+    for name in ("api", "extraction", "peer"):
         obj = os.path.join(OBJDIR, name + ".o")
         objs.append(obj)
         src = os.path.join(CSRC, name + ".cu")

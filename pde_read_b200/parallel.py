@@ -8,12 +8,18 @@ the points with replicated weights and the exchange is ONE small all-reduce:
   * discovery : float32 [dU | dN | sum(R^2) as a (hi, lo) float pair]   (84 KB .. 330 KB)
   * extraction: float64 [G | A^T b | b^T b]                               (3 KB .. 508 KB)
 
-These payloads are latency-bound on NVLink/NVSwitch, so NCCL's all-reduce is used as is (there is
-no compute step to fuse the transfer with tile by tile).  The backend is whatever the process
-group was created with: "nccl" on GPUs, "gloo" in the CPU tests of this logic.
+These payloads are latency-bound on NVLink/NVSwitch.  The discovery exchange -- once per training step -- runs on
+the library's own one-shot all-reduce over peer memory when every rank sits on one box (PeerAllReduce below:
+each rank writes its buffer into every peer's receive area and sums its own area in rank order; one kernel, no
+NCCL on the step), and on NCCL's all-reduce otherwise; the extraction sums, once per run, stay on NCCL.  The
+backend is whatever the process group was created with: "nccl" on GPUs, "gloo" in the CPU tests of this logic.
 """
 from __future__ import annotations
 
+import ctypes
+import os
+import socket
+import zlib
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -35,6 +41,59 @@ def shard_points(coords: torch.Tensor, rank: int, world_size: int) -> torch.Tens
     return coords[lo:hi].contiguous()
 
 
+class PeerAllReduce:
+    """In-place sum of a float32 CUDA buffer over the ranks of one box through peer memory
+    (csrc/peer.cu, pderead_peer_allreduce).  Construction is a collective: every rank allocates its receive area,
+    the CUDA IPC handles travel through the process group once, and all ranks agree on success; `ok` is False
+    (on every rank alike) when the ranks span several hosts, peer mapping fails, or PDEREAD_PEER_ALLREDUCE=0."""
+
+    def __init__(self, group, cap_floats: int):
+        from . import _lib
+        self.ok = False
+        self.group, self.cap = group, int(cap_floats + 3) // 4 * 4
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self._lib, self._areas, self._local = _lib.load(), [], None
+        dev = torch.device("cuda", torch.cuda.current_device())
+        want = os.environ.get("PDEREAD_PEER_ALLREDUCE", "1") != "0" and 1 < self.world <= 32
+        handle = (ctypes.c_ubyte * 64)()
+        local = ctypes.c_void_p()
+        good = want
+        if good:
+            good = self._lib.pderead_peer_alloc(self.world, self.cap, ctypes.byref(local), handle) == 0
+        # one exchange carries the handle, the host name (hashed) and this rank's verdict so far
+        host = zlib.crc32(socket.gethostname().encode()) & 0xFFFFFF
+        # (an all-reduce of a one-hot [world, 68] table, not an all-gather: NCCL_ALGO=Tree has no all-gather)
+        table = torch.zeros(self.world, 68, dtype=torch.int32, device=dev)
+        table[self.rank] = torch.tensor(list(bytes(handle)) + [host >> 16 & 255, host >> 8 & 255, host & 255, 1 if good else 0],
+                                        dtype=torch.int32, device=dev)
+        dist.all_reduce(table, op=dist.ReduceOp.SUM, group=group)
+        rows = [bytes(r) for r in table.cpu().tolist()]
+        good = good and all(r[67] == 1 for r in rows) and all(r[64:67] == rows[0][64:67] for r in rows)
+        if good:
+            for r, row in enumerate(rows):
+                if r == self.rank:
+                    self._areas.append(local.value)
+                    continue
+                p = ctypes.c_void_p()
+                hb = (ctypes.c_ubyte * 64).from_buffer_copy(row[:64])
+                if self._lib.pderead_peer_open(hb, ctypes.byref(p)) != 0:
+                    good = False
+                    break
+                self._areas.append(p.value)
+        flag = torch.tensor([1 if good else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.ok = bool(int(flag.item()))
+        self._local = local.value
+        if self.ok:
+            self._table = torch.tensor(self._areas, dtype=torch.int64, device=dev)
+
+    def allreduce_(self, flat: torch.Tensor) -> None:
+        from . import _lib
+        stream = torch.cuda.current_stream(flat.device).cuda_stream
+        _lib.check(self._lib.pderead_peer_allreduce(flat.data_ptr(), flat.numel(), self._table.data_ptr(), self._local,
+                                                    self.rank, self.world, self.cap, stream), "pderead_peer_allreduce")
+
+
 class ShardReducer:
     """All-reduce helper handed to Collocation_Loss (via Loss_Functions.set_reducer) and to
     Extraction.Extract_PDE.
@@ -52,6 +111,19 @@ class ShardReducer:
         self.group = group
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self._peer = None           # PeerAllReduce, built at the first gradient exchange (a collective, like that exchange)
+
+    def _sum_flat(self, flat: torch.Tensor) -> None:
+        """In-place sum of the packed float32 buffer over the ranks: peer memory on one box, else NCCL / gloo.  Which one
+        is decided collectively (PeerAllReduce.ok is the same on every rank; buffer sizes are the same on every rank)."""
+        if flat.is_cuda and dist.get_backend(self.group) == "nccl":
+            n = flat.numel()
+            if self._peer is None or (self._peer.ok and n > self._peer.cap):
+                self._peer = PeerAllReduce(self.group, max(n, 1 << 17))
+            if self._peer.ok and n % 4 == 0 and flat.data_ptr() % 16 == 0:
+                self._peer.allreduce_(flat)
+                return
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
 
     def total_points(self, local_points: int) -> int:
         """Sum of the ranks' local point counts.  Always a collective (every rank must call it); returns a
@@ -86,7 +158,7 @@ class ShardReducer:
             ss = sum_sq if (sum_sq.dtype == torch.float64 and sum_sq.is_cuda) else sum_sq.to(flat.device, torch.float64)
             _lib.check(lib.pderead_loss_tail_pack(ss.data_ptr(), int(local_points), tail.data_ptr(), stream),
                        "pderead_loss_tail_pack")
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            self._sum_flat(flat)
             _lib.check(lib.pderead_loss_tail_unpack(tail.data_ptr(), M_as, out.data_ptr(), stream),
                        "pderead_loss_tail_unpack")
             return out
