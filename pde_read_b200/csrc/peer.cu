@@ -135,7 +135,14 @@ int pderead_peer_open(const unsigned char* handle64, void** d_area) {
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, 64);
     void* p = nullptr;
-    PDR_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        // (a peer that is not visible to this process, or no peer access: the caller falls back to NCCL -- do not
+        //  leave the error behind for the next launch check to trip over)
+        set_last_cuda_error(e, __FILE__, __LINE__);
+        (void)cudaGetLastError();
+        return PDEREAD_ERR_CUDA;
+    }
     *d_area = p;
     return PDEREAD_OK;
 }
