@@ -19,12 +19,6 @@ constexpr int THP = 8;          // pair tile: half chunk padded to two 16-byte w
 constexpr int TNP_PAIR = 2 * THP;   // packed floats per chunk and row, pair tile: [half][THP]
 constexpr int TNP_LANE = 12;        // packed floats per chunk and row, lane tile (keeps rows 16-byte aligned)
 constexpr int TNP = TNP_PAIR;       // workspace sizing: the larger of the two
-#ifndef PDR_W_EVICT_LAST
-#define PDR_W_EVICT_LAST 0          // weight loads of the layer products with the L1 evict_last hint
-#endif
-#ifndef PDR_STASH_CS
-#define PDR_STASH_CS 0              // forward kernel: streaming stores for the stash
-#endif
 #ifndef PDR_PROD_UNROLL
 #define PDR_PROD_UNROLL 2           // unroll factor of the layer-product loop
 #endif

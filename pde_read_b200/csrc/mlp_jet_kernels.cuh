@@ -46,27 +46,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-// Weight loads of the layer products: read-only path, and (PDR_W_EVICT_LAST) kept in L1 in preference to everything
-// else that passes through it.
-__device__ __forceinline__ float4 ldg_w4(const float4* p) {
-#if PDR_W_EVICT_LAST
-    float4 v;
-    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-#else
-    return __ldg(p);
-#endif
-}
-__device__ __forceinline__ float ldg_w1(const float* p) {
-#if PDR_W_EVICT_LAST
-    float v;
-    asm volatile("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-#else
-    return __ldg(p);
-#endif
-}
-
 template <int ACT>
 __device__ __forceinline__ void load_ab(const NetDev& net, int l, float* ab) {
     if (ACT == ACT_RATIONAL) {
@@ -206,8 +185,8 @@ struct ProdTile<true, PPL, J> {
     // wk: this thread's weights of row k
     template <int JP, bool WS>
     __device__ __forceinline__ void step(const float* __restrict__ hk, const float* __restrict__ wk) {
-        const float4 w4 = WS ? *reinterpret_cast<const float4*>(wk) : ldg_w4(reinterpret_cast<const float4*>(wk));
-        const float w5 = WS ? wk[4] : ldg_w1(wk + 4);
+        const float4 w4 = WS ? *reinterpret_cast<const float4*>(wk) : __ldg(reinterpret_cast<const float4*>(wk));
+        const float w5 = WS ? wk[4] : __ldg(wk + 4);
         const float wv[TH] = {w4.x, w4.y, w4.z, w4.w, w5};
         float hv[QP][J];
 #pragma unroll
@@ -256,9 +235,9 @@ struct ProdTile<false, PPL, J> {
     template <int JP, bool WS>
     __device__ __forceinline__ void step(const float* __restrict__ hk, const float* __restrict__ wk) {
         const float4* w4p = reinterpret_cast<const float4*>(wk);
-        const float4 b0 = WS ? w4p[0] : ldg_w4(w4p);
-        const float4 b1 = WS ? w4p[1] : ldg_w4(w4p + 1);
-        const float4 b2 = WS ? w4p[2] : ldg_w4(w4p + 2);
+        const float4 b0 = WS ? w4p[0] : __ldg(w4p);
+        const float4 b1 = WS ? w4p[1] : __ldg(w4p + 1);
+        const float4 b2 = WS ? w4p[2] : __ldg(w4p + 2);
         const float2 bw[TNP_LANE / 2] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
                                          make_float2(b1.z, b1.w), make_float2(b2.x, b2.y), make_float2(b2.z, b2.w)};
 #pragma unroll
@@ -304,24 +283,6 @@ __device__ __forceinline__ void stash_store(float* p, const float* z) {
 #pragma unroll
         for (int j = 0; j < J; ++j) p[j] = z[j];
     }
-}
-// the forward kernel's stash rows go to HBM and are not read again by this kernel: streaming stores
-template <int J>
-__device__ __forceinline__ void stash_store_global(float* p, const float* z) {
-#if PDR_STASH_CS
-    if constexpr (J % 4 == 0) {
-#pragma unroll
-        for (int j = 0; j < J; j += 4) __stcs(reinterpret_cast<float4*>(p + j), make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]));
-    } else if constexpr (J % 2 == 0) {
-#pragma unroll
-        for (int j = 0; j < J; j += 2) __stcs(reinterpret_cast<float2*>(p + j), make_float2(z[j], z[j + 1]));
-    } else {
-#pragma unroll
-        for (int j = 0; j < J; ++j) __stcs(p + j, z[j]);
-    }
-#else
-    stash_store<J>(p, z);
-#endif
 }
 template <int J>
 __device__ __forceinline__ void stash_load(const float* p, float* z) {
@@ -508,7 +469,7 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_fwd_
                             act_fwd<ACT, NX, NT, float>(z, ab, y);
                             if (STASH) {
                                 if (ACT == ACT_TANH) z[0] = y[0];       // see "rows of the reverse pass"
-                                stash_store_global<J>(a.stash + (((size_t)tile * (L - 1) + (l - 1)) * W + i) * (J * TP) + pt * J, z);
+                                stash_store<J>(a.stash + (((size_t)tile * (L - 1) + (l - 1)) * W + i) * (J * TP) + pt * J, z);
                             }
                             if (last) {
 #pragma unroll
@@ -885,8 +846,8 @@ __global__ void __launch_bounds__(RegCap<1 + NX + NT>::max_threads) mlp_jet_bwd_
                 Tile acc;
                 acc.zero();
                 if (stage) product_loop<J, true>(acc, Zb + Tile::point(lane, 0) * J, HS, WSB + Tile::wofs(lane, c), NC * Tile::WROW, W);
-                // (weight rows requested two k-steps ahead in registers -- the reverse kernel's weights come from L2 --
-                //  were measured: 0.697 ms against 0.663 at C2)
+                // (measured without effect or with a loss, see DESIGN.md section 4: weight rows requested two k-steps ahead
+                //  in registers, L1::evict_last on the weight loads, streaming stores for the forward's stash)
                 else       product_loop<J, false>(acc, Zb + Tile::point(lane, 0) * J, HS, wp + Tile::wofs(lane, c), NC * Tile::WROW, W);
                 // (requesting the stash rows of the VJP one neuron ahead, the first ones before the product loop, was
                 //  measured: reverse-U at C2 0.697 ms against 0.662 -- the 8 extra live registers cost more than the latency)
