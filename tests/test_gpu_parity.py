@@ -638,3 +638,36 @@ def test_input_batch_norm_sharded_matches_single_process():
         got = outs[0][1][k] + outs[1][1][k]
         assert np.abs(got - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-3 * scale), k
     assert torch.allclose(outs[0][2], want_rm, rtol=1e-5, atol=1e-7) and torch.allclose(outs[1][2], want_rm, rtol=1e-5, atol=1e-7)
+
+
+def test_kernel_variants_are_selected_by_shape():
+    """The instantiations behind one entry point (forward: plain / staged weights / spilled buffers = last template
+    argument 0 / 1 / 2; reverse: ..., spilled = last argument) are picked from the network shape: C2's 5 x 50 keeps
+    everything in shared memory with weights through the read-only path, 5 x 100 at n = 4 stages its weights, width 420
+    spills its activation buffers to the workspace; the narrow PDE network runs the three-CTA plain kernels."""
+    from torch.profiler import ProfilerActivity, profile
+    from pde_read_b200 import functional as F
+
+    def names(fn):
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        return [e.key.replace(" ", "").replace("true", "1").replace("false", "0") for e in prof.key_averages()]
+
+    def step(act, LU, WU, LN, WN, m, n, M=300):
+        su, sn = orc.init_network(LU, WU, 2, act, seed=3), orc.init_network(LN, WN, n + 1, act, seed=4)
+        U, N = make_net(su, act, 2), make_net(sn, act, n + 1)
+        P = (torch.rand(M, 2, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(DEV)
+        return names(lambda: F.collocation_loss_grad(F.net_spec(U), F.net_tensors(U), F.net_spec(N), F.net_tensors(N), m, n, P))
+
+    got = step("Tanh", 5, 50, 5, 50, 1, 2)
+    assert any(k.startswith("voidpdr::mlp_jet_fwd_kernel<0,2,1,1,1,0>") for k in got), got
+    assert any(k.startswith("voidpdr::mlp_jet_bwd_kernel<0,2,1,1,0>") for k in got), got
+    assert any(k.startswith("voidpdr::mlp_plain_fwd_kernel<0,1,2,1>") or k.startswith("voidpdr::mlp_plain_fwd_kernel<0,1,4,1>")
+               for k in got), got                                                                # narrow: three CTAs per SM
+    got = step("Rational", 5, 100, 5, 100, 1, 4)
+    assert any(k.startswith("voidpdr::mlp_jet_fwd_kernel<2,4,1,1,1,1>") for k in got), got       # staged weights
+    assert any(k.startswith("voidpdr::mlp_jet_bwd_kernel<2,4,1,0,0>") for k in got), got         # wide block, in shared memory
+    got = step("Sin", 2, 420, 1, 8, 1, 1)
+    assert any(k.startswith("voidpdr::mlp_jet_fwd_kernel<1,1,1,1,1,2>") for k in got), got       # spilled buffers
+    assert any(k.startswith("voidpdr::mlp_jet_bwd_kernel<1,1,1,") and k.split("(")[0].endswith(",1>") for k in got), got
