@@ -203,3 +203,37 @@ def test_timer():
         t.Stop()
     t.Start()
     assert t.Stop() >= 0.0
+
+
+def test_hot_kernels_keep_their_register_budget():
+    """Occupancy of the bench kernels rests on register caps (96 registers -> four CTAs of the C2 U kernels per SM,
+    80 -> three CTAs of the narrow plain-MLP kernels, 128 for the long-jet kernels) with no or next to no spilling;
+    a change that makes ptxas spill shows up here (cuobjdump on the built library, no GPU needed) instead of as an
+    unexplained slowdown -- it happened once this round: reverse-U 0.66 -> 0.94 ms with 88 bytes of stack."""
+    import re
+    import shutil
+    import subprocess
+    from pde_read_b200 import build as B
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    if not os.path.exists(B.LIB):
+        pytest.skip("library not built")
+    out = subprocess.run([tool, "--dump-resource-usage", B.LIB], capture_output=True, text=True).stdout
+    use = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
+        use[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+    want = {   # mangled kernel: (max registers, max stack bytes)
+        "_ZN3pdr18mlp_jet_fwd_kernelILi0ELi2ELi1ELb1ELi1ELi0EEEvNS_7FwdArgsE": (96, 16),    # C2 U forward (stash)
+        "_ZN3pdr18mlp_jet_bwd_kernelILi0ELi2ELi1ELb1ELb0EEEvNS_7BwdArgsE": (96, 16),        # C2 U reverse (fused)
+        "_ZN3pdr18mlp_jet_fwd_kernelILi2ELi2ELi0ELb0ELi1ELi0EEEvNS_7FwdArgsE": (96, 16),    # C5 U forward (x-series)
+        "_ZN3pdr18mlp_jet_fwd_kernelILi2ELi3ELi1ELb1ELi1ELi0EEEvNS_7FwdArgsE": (128, 16),   # C3 U forward
+        "_ZN3pdr18mlp_jet_bwd_kernelILi2ELi3ELi1ELb1ELb0EEEvNS_7BwdArgsE": (128, 16),       # C3 U reverse
+        "_ZN3pdr18mlp_jet_fwd_kernelILi2ELi4ELi1ELb1ELi1ELi1EEEvNS_7FwdArgsE": (128, 16),   # C4 U forward (staged weights)
+        "_ZN3pdr18mlp_jet_bwd_kernelILi2ELi4ELi1ELb0ELb0EEEvNS_7BwdArgsE": (128, 16),       # C4 U reverse (wide block)
+        "_ZN3pdr20mlp_plain_fwd_kernelILi0ELb1ELi4ELb1EEEvNS_7FwdArgsE": (80, 32),          # C2 N forward (narrow)
+        "_ZN3pdr20mlp_plain_bwd_kernelILi0ELb1EEEvNS_7BwdArgsE": (80, 48),                  # C2 N reverse (narrow)
+    }
+    for name, (regs, stack) in want.items():
+        assert name in use, "kernel not found in the library: %s" % name
+        assert use[name][0] <= regs and use[name][1] <= stack, (name, use[name], (regs, stack))
