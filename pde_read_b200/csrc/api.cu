@@ -169,55 +169,91 @@ size_t bwd_smem_small(int W, int L, int din, int J) {
 // pair tile:  wt[l][k][c*TNP_PAIR+b*THP+n] = W_{l+1}[c*TN+b*TH+n][k]   (transposed, for z = W h)
 //             wn[l][i][c*TNP_PAIR+b*THP+n] = W_{l+1}[i][c*TN+b*TH+n]   (native,     for hbar = W^T zbar)
 // lane tile:  wt[l][k][c*TNP_LANE+n] = W_{l+1}[c*TN+n][k],  wn[l][i][c*TNP_LANE+n] = W_{l+1}[i][c*TN+n]
-__global__ void pack_weights_kernel(NetDev net, int pair, float* wt, float* wn) {
+__global__ void pack_weights_kernel(NetDev net, int pair, float* wt, float* wn);
+
+// ---- element functions of the two weight layouts (shared by the single-job kernels and pack_jobs_kernel) --------
+__device__ __forceinline__ void pack_jet_element(const NetDev& net, int pair, float* wt, float* wn, size_t idx) {
     const int W = net.W, NC = net.NC;
-    const int TNP = pair ? TNP_PAIR : TNP_LANE;
-    const size_t per_layer = (size_t)W * NC * TNP;
-    const size_t total = per_layer * (net.L - 1);
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (size_t)gridDim.x * blockDim.x) {
-        const int l = (int)(idx / per_layer);
-        const size_t rem = idx - (size_t)l * per_layer;
-        const int row = (int)(rem / (NC * TNP));
-        const int col = (int)(rem - (size_t)row * (NC * TNP));
-        const int c = col / TNP, pos = col - c * TNP;
-        int o;
-        bool ok;
-        if (pair) {
-            const int half = pos / THP, n = pos - half * THP;
-            o = c * TN + half * TH + n;
-            ok = (n < TH) && (o < W);
-        } else {
-            o = c * TN + pos;
-            ok = (pos < TN) && (o < W);
-        }
-        const float* w = net.w[l + 1];
-        if (wt) wt[idx] = ok ? w[(size_t)o * W + row] : 0.f;
-        if (wn) wn[idx] = ok ? w[(size_t)row * W + o] : 0.f;
+    const int TNPk = pair ? TNP_PAIR : TNP_LANE;
+    const size_t per_layer = (size_t)W * NC * TNPk;
+    const int l = (int)(idx / per_layer);
+    const size_t rem = idx - (size_t)l * per_layer;
+    const int row = (int)(rem / (NC * TNPk));
+    const int col = (int)(rem - (size_t)row * (NC * TNPk));
+    const int c = col / TNPk, pos = col - c * TNPk;
+    int o;
+    bool ok;
+    if (pair) {
+        const int half = pos / THP, n = pos - half * THP;
+        o = c * TN + half * TH + n;
+        ok = (n < TH) && (o < W);
+    } else {
+        o = c * TN + pos;
+        ok = (pos < TN) && (o < W);
     }
+    const float* w = net.w[l + 1];
+    if (wt) wt[idx] = ok ? w[(size_t)o * W + row] : 0.f;
+    if (wn) wn[idx] = ok ? w[(size_t)row * W + o] : 0.f;
+}
+__device__ __forceinline__ void pack_plain_element(const NetDev& net, int WP, int native, float* wt, size_t idx) {
+    const int W = net.W;
+    const size_t per_layer = (size_t)W * WP;
+    const int l = (int)(idx / per_layer);
+    const size_t rem = idx - (size_t)l * per_layer;
+    const int r = (int)(rem / WP), c = (int)(rem - (size_t)r * WP);
+    float v = 0.f;
+    if (c < W) v = native ? net.w[l + 1][(size_t)r * W + c] : net.w[l + 1][(size_t)c * W + r];
+    wt[idx] = v;
+}
+
+__global__ void pack_weights_kernel(NetDev net, int pair, float* wt, float* wn) {
+    const size_t total = (size_t)net.W * net.NC * (pair ? TNP_PAIR : TNP_LANE) * (net.L - 1);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+        pack_jet_element(net, pair, wt, wn, idx);
 }
 
 // plain-MLP forward kernel (mlp_plain_kernels.cuh): wt[l][k][i] = W_{l+1}[i][k], rows padded with zeros to WP
 // (native != 0: wn[l][i][k] = W_{l+1}[i][k], the layout of the plain reverse kernel)
 __global__ void pack_plain_weights_kernel(NetDev net, int WP, int native, float* wt) {
-    const int W = net.W;
-    const size_t per_layer = (size_t)W * WP, total = per_layer * (net.L - 1);
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int l = (int)(idx / per_layer);
-        const size_t rem = idx - (size_t)l * per_layer;
-        const int r = (int)(rem / WP), c = (int)(rem - (size_t)r * WP);
-        float v = 0.f;
-        if (c < W) v = native ? net.w[l + 1][(size_t)r * W + c] : net.w[l + 1][(size_t)c * W + r];
-        wt[idx] = v;
+    const size_t total = (size_t)net.W * WP * (net.L - 1);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+        pack_plain_element(net, WP, native, wt, idx);
+}
+
+// All weight images of a fused step in ONE launch (blockIdx.y = job): the collocation step packs U (transposed +
+// native, jet layout) and N (transposed + native, plain or jet layout) -- three or four ~10 us launches otherwise,
+// 2 % of the C2 step and 5 % of the C1 step.
+struct PackJob {
+    NetDev net;
+    int kind;        // 0: jet layout (a = wt, b = wn, arg = pair tile?), 1: plain layout (a = dst, arg = native?, wp)
+    int arg, wp;
+    float *a, *b;
+    unsigned long long total;
+};
+struct PackJobs {
+    PackJob j[4];
+    int n;
+};
+__global__ void pack_jobs_kernel(const PackJobs jobs) {
+    const PackJob& jb = jobs.j[blockIdx.y];
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < jb.total; idx += (size_t)gridDim.x * blockDim.x) {
+        if (jb.kind == 0) pack_jet_element(jb.net, jb.arg, jb.a, jb.b, idx);
+        else              pack_plain_element(jb.net, jb.wp, jb.arg, jb.a, idx);
     }
 }
 
 // dst = beta*dst + scale * sum_over_parts(gpart).  Block = 32 consecutive elements x 8 slices of the partial
 // vectors; every thread sums its slice with four independent accumulators (the loads are the cost), the
 // slices are combined through shared memory in a fixed order, so the result is bit-reproducible.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ gpart, int nparts, int stride,
-                                                              SegmentTable tab, float beta, float scale) {
-    __shared__ float red[8][33];
+struct ReduceJob {
+    const float* gpart;
+    int nparts, stride;
+    SegmentTable tab;
+    float beta, scale;
+};
+__device__ __forceinline__ void reduce_partials_body(const ReduceJob& jb, float (&red)[8][33]) {
+    const float* __restrict__ gpart = jb.gpart;
+    const int nparts = jb.nparts, stride = jb.stride;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + tx;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -235,14 +271,27 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     __syncthreads();
     if (ty == 0 && e < stride) {
         int s = -1;
-        for (int t = 0; t < tab.n; ++t)
-            if (e >= tab.seg[t].off && e < tab.seg[t].off + tab.seg[t].count) { s = t; break; }
+        for (int t = 0; t < jb.tab.n; ++t)
+            if (e >= jb.tab.seg[t].off && e < jb.tab.seg[t].off + jb.tab.seg[t].count) { s = t; break; }
         if (s < 0) return;
         float acc = 0.f;
 #pragma unroll
         for (int y = 0; y < 8; ++y) acc += red[y][tx];
-        float* d = tab.seg[s].dst + (e - tab.seg[s].off);
-        *d = (beta == 0.f ? 0.f : beta * (*d)) + scale * acc;
+        float* d = jb.tab.seg[s].dst + (e - jb.tab.seg[s].off);
+        *d = (jb.beta == 0.f ? 0.f : jb.beta * (*d)) + jb.scale * acc;
+    }
+}
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceJob jb) {
+    __shared__ float red[8][33];
+    reduce_partials_body(jb, red);
+}
+// both networks of a fused step in one launch (blockIdx.y picks the network; same arithmetic, same fixed order)
+__global__ void __launch_bounds__(256) reduce_partials2_kernel(const ReduceJob j0, const ReduceJob j1) {
+    __shared__ float red[8][33];
+    if (blockIdx.y == 0) {
+        if (blockIdx.x * 32 < j0.stride) reduce_partials_body(j0, red);
+    } else {
+        if (blockIdx.x * 32 < j1.stride) reduce_partials_body(j1, red);
     }
 }
 
@@ -1018,7 +1067,20 @@ static int dispatch_plain_bwd(int act, const BwdArgs& a, int grid, cudaStream_t 
 static int reduce_partials(const float* gpart, int nparts, const GradLayout& lay, const SegmentTable& tab, float beta,
                            float scale, cudaStream_t s) {
     const int blocks = (lay.total + 31) / 32;
-    reduce_partials_kernel<<<blocks, 256, 0, s>>>(gpart, nparts, lay.total, tab, beta, scale);
+    ReduceJob jb;
+    jb.gpart = gpart; jb.nparts = nparts; jb.stride = lay.total; jb.tab = tab; jb.beta = beta; jb.scale = scale;
+    reduce_partials_kernel<<<blocks, 256, 0, s>>>(jb);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark(s, ST_REDUCE);
+    return PDEREAD_OK;
+}
+static int reduce_partials2(const float* gp0, int np0, const GradLayout& l0, const SegmentTable& t0, const float* gp1,
+                            int np1, const GradLayout& l1, const SegmentTable& t1, float beta, float scale, cudaStream_t s) {
+    ReduceJob a, b;
+    a.gpart = gp0; a.nparts = np0; a.stride = l0.total; a.tab = t0; a.beta = beta; a.scale = scale;
+    b.gpart = gp1; b.nparts = np1; b.stride = l1.total; b.tab = t1; b.beta = beta; b.scale = scale;
+    const int bx = ((l0.total > l1.total ? l0.total : l1.total) + 31) / 32;
+    reduce_partials2_kernel<<<dim3(bx, 2), 256, 0, s>>>(a, b);
     PDR_CUDA_CHECK(cudaGetLastError());
     stage_mark(s, ST_REDUCE);
     return PDEREAD_OK;
@@ -1250,6 +1312,46 @@ static int plan_backward(const NetDev& n, int act, int nx, int nt, bool want_gin
     }
     p->gpart = cv.take<float>((size_t)p->grid * lay.total);
     return cv.ok ? PDEREAD_OK : PDEREAD_ERR_WORKSPACE_TOO_SMALL;
+}
+
+// ---- the same weight images as jobs of one pack_jobs_kernel launch (fused collocation step) -------------------
+static void add_jet_job(PackJobs& js, const NetDev& n, int J, float* wt, float* wn) {
+    if (n.L <= 1 || (!wt && !wn)) return;
+    PackJob& j = js.j[js.n++];
+    j.net = n; j.kind = 0; j.arg = use_pair_map(J) ? 1 : 0; j.wp = 0; j.a = wt; j.b = wn;
+    j.total = (unsigned long long)(n.L - 1) * n.W * n.NC * (j.arg ? TNP_PAIR : TNP_LANE);
+}
+static void add_plain_job(PackJobs& js, const NetDev& n, float* dst, int native) {
+    if (n.L <= 1 || !dst) return;
+    PackJob& j = js.j[js.n++];
+    j.net = n; j.kind = 1; j.arg = native; j.wp = plain_wp_h(n.W); j.a = dst; j.b = nullptr;
+    j.total = (unsigned long long)(n.L - 1) * n.W * j.wp;
+}
+// false: this plan packs something the job kernel does not know (tensor-core weight images)
+static bool forward_pack_jobs(const NetDev& n, const FwdPlan& p, PackJobs& js) {
+    if (p.tc) return false;
+    if (p.plain) add_plain_job(js, n, p.wt, 0);
+    else         add_jet_job(js, n, p.J, p.wt, nullptr);
+    return true;
+}
+static void backward_pack_jobs(const NetDev& n, const BwdPlan& p, PackJobs& js) {
+    if (p.fwd.plain) {
+        add_plain_job(js, n, p.fwd.wt, 0);
+        if (p.plain) add_plain_job(js, n, p.wn, 1);
+        else         add_jet_job(js, n, p.fwd.J, nullptr, p.wn);
+    } else {
+        add_jet_job(js, n, p.fwd.J, p.fwd.wt, p.wn);
+    }
+}
+static int launch_pack_jobs(const PackJobs& js, cudaStream_t s) {
+    if (js.n == 0) return PDEREAD_OK;
+    unsigned long long most = 0;
+    for (int i = 0; i < js.n; ++i) most = js.j[i].total > most ? js.j[i].total : most;
+    const unsigned bx = (unsigned)((most + 255) / 256 < 592 ? (most + 255) / 256 : 592);
+    pack_jobs_kernel<<<dim3(bx, js.n), 256, 0, s>>>(js);
+    PDR_CUDA_CHECK(cudaGetLastError());
+    stage_mark(s, ST_PACK);
+    return PDEREAD_OK;
 }
 
 static int plan_backward_pack(const NetDev& n, const BwdPlan& p, cudaStream_t s) {
@@ -1497,12 +1599,18 @@ static int residual_impl(const pderead_net* sol, const pderead_net* pde, int m, 
     }
     if (!cv.ok) return PDEREAD_ERR_WORKSPACE_TOO_SMALL;
 
-    if (backward) {
-        if ((rc = plan_backward_pack(U, bU, s))) return rc;
-        if ((rc = plan_backward_pack(N, bN, s))) return rc;
-    } else {
-        if ((rc = plan_pack(U, fU, s))) return rc;
-        if ((rc = plan_pack(N, fN, s))) return rc;
+    {
+        // one launch for every weight image of the step (the tensor-core forward's images keep their own kernel)
+        PackJobs js;
+        memset(&js, 0, sizeof(js));
+        if (backward) {
+            backward_pack_jobs(U, bU, js);
+            backward_pack_jobs(N, bN, js);
+        } else {
+            if (!forward_pack_jobs(U, fU, js) && (rc = plan_pack(U, fU, s))) return rc;
+            if (!forward_pack_jobs(N, fN, js) && (rc = plan_pack(N, fN, s))) return rc;
+        }
+        if ((rc = launch_pack_jobs(js, s))) return rc;
     }
 
     bool first = true;
@@ -1561,8 +1669,7 @@ static int residual_impl(const pderead_net* sol, const pderead_net* pde, int m, 
         first = false;
     }
     if (backward) {
-        if ((rc = reduce_partials(bU.gpart, bU.grid, lu, tu, beta, 1.f, s))) return rc;
-        if ((rc = reduce_partials(bN.gpart, bN.grid, ln, tn, beta, 1.f, s))) return rc;
+        if ((rc = reduce_partials2(bU.gpart, bU.grid, lu, tu, bN.gpart, bN.grid, ln, tn, beta, 1.f, s))) return rc;
     }
     return PDEREAD_OK;
 }
