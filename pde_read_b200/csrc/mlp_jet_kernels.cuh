@@ -8,17 +8,18 @@
 // by propagating the x-/t-series of every neuron through the layers (jet_math.cuh) and by the
 // hand-written adjoint of that propagation.
 //
-// Thread mapping ("lane = point"): a CTA owns a tile of TP = 32*PPL points; lane l of every warp
-// owns points l, l+32, ..; warp w owns chunks of TN output neurons.  In the layer product
+// A CTA owns a tile of TP = 32*PPL points and walks all layers of the network for it; a warp owns a chunk of TN = 10
+// output neurons.  In the layer product
 //   z_j[i] = sum_k W[i][k] h_j[k]      (j = jet index, i = output neuron)
-// a thread keeps PPL*J*TN accumulators in registers, reads the jet h[k] of its own points from shared
-// memory (rows [neuron][point][jet]: one vector access per point, conflict-free) and the TN weights
-// W[i0..][k] through the read-only path (same address in all lanes -> one broadcast transaction).  The
-// activation jets are then applied to the accumulators in registers; activations never go to HBM
-// except for the pre-activation stash the reverse pass needs.
+// a thread keeps 10 (neuron, point) jets as accumulators in registers, reads the jets h[k] of its points from shared
+// memory (rows [neuron][point][jet]) and its weights W[.][k] either through the read-only path or from a slice staged
+// in shared memory by cp.async; which (neuron, point) pairs a thread owns depends on the jet length (ProdTile: the
+// pair tile for J <= 4, the lane tile above).  The activation jets are applied to the accumulators in registers;
+// activations never go to HBM except for the pre-activation stash the reverse pass needs (and, for networks too wide
+// for shared memory, the SPILL instantiations that keep the tile's buffers in the workspace).
 //
 // Reverse pass, per layer (two shared buffers Zb / Yb that swap roles): weight + bias gradients as a
-// register-tiled product of the two buffers; ybar = W^T zbar with the forward mapping and the activation
+// register-tiled product of the two buffers; ybar = W^T zbar with the forward's tile and the activation
 // VJP in its epilogue (ybar never leaves the registers); activations of the layer below from the stash.
 #pragma once
 #include <cuda_runtime.h>
