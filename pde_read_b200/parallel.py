@@ -86,6 +86,14 @@ class PeerAllReduce:
         self._local = local.value
         if self.ok:
             self._table = torch.tensor(self._areas, dtype=torch.int64, device=dev)
+        else:
+            # not usable (on every rank alike): give the mappings and the area back, the caller stays on NCCL
+            for r, p in enumerate(self._areas):
+                if r != self.rank and p:
+                    self._lib.pderead_peer_close(ctypes.c_void_p(p))
+            if local.value:
+                self._lib.pderead_peer_free(local)
+            self._areas, self._local = [], None
 
     def allreduce_(self, flat: torch.Tensor) -> None:
         from . import _lib
